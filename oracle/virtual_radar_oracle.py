@@ -1,0 +1,211 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU oracle for the VirtualRadar hot path.
+
+A restatement, stage by stage, of `VirtualRadar.forward` (reference
+layers/virtual_radar.py:79-134) with the same ATen CPU ops in the same order, so that on
+identical inputs it reproduces the reference's float32 results.  The reference file itself is
+not shipped (it cannot travel to the GPU box and must not be copied); instead this port is
+PINNED against outputs of the real reference run in the build container:
+tests/golden/make_golden.py imports /root/reference/layers/virtual_radar.py verbatim (with
+oracle/nnaudio_stft.py standing in for the absent nnAudio dependency) and commits small
+input/output fixtures; tests/test_oracle.py checks this port against them bit for bit, and
+against the known-answers of BASELINE.md section 3 (rows A-E).
+
+Variants:
+  forward(..., dtype=torch.float32, distance='aten')   "ref-f32": THE parity target.  `distance`
+        picks how the rounding-critical radar->joint range is formed:
+          'aten' : torch.norm(dim=1) on the tensor as laid out (what the reference does; its
+                   rounding depends on x.stride(1)),
+          'seq' / 'fma' : the explicit C recipes of oracle/range_phase.c -- machine independent;
+                   this is what the GPU parity tests use, with the mode chosen from the strides
+                   by `distance_mode_for(x)`.
+  forward(..., dtype=torch.float64)                    "truth-f64": same graph in double, with
+        the float32-rounded parameter values.
+
+Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline leg, --impl reference) may
+import this module.  The product (skeleton_action_recognition_b200) never does.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import torch
+
+from .nnaudio_stft import STFT
+
+# default bone list of the reference (layers/virtual_radar.py:10-13): NTU RGB+D skeleton,
+# 24 bones over 25 joints.  Written as (parent -> children) chains, same pairs, same order.
+NTU_EDGES = [(0, 1), (1, 20), (20, 2), (2, 3),
+             (20, 4), (4, 5), (5, 6), (6, 7), (7, 21), (7, 22),
+             (20, 8), (8, 9), (9, 10), (10, 11), (11, 23), (11, 24),
+             (0, 16), (0, 12), (12, 13), (13, 14), (14, 15),
+             (16, 17), (17, 18), (18, 19)]
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build_c(force=False):
+    """Compile oracle/range_phase.c -> oracle/_build/librange_phase.so (gcc, a second or so)."""
+    so = os.path.join(_HERE, "_build", "librange_phase.so")
+    src = os.path.join(_HERE, "range_phase.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.run(["make", "-s", "-C", _HERE, "-B", "_build/librange_phase.so"], check=True)
+    return so
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        lib = ctypes.CDLL(build_c())
+        lib.vr_oracle_range_phase.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                                              ctypes.c_float, ctypes.c_int, ctypes.c_void_p,
+                                              ctypes.c_void_p]
+        lib.vr_oracle_range_phase.restype = None
+        _LIB = lib
+    return _LIB
+
+
+def distance_mode_for(x):
+    """'fma' when the coordinate axis is the innermost stride (notebook-style tensors built from
+    a (T,V,C) array), else 'seq' -- SURVEY.md fact 6 / Appendix C layout rule."""
+    return "fma" if (x.dim() == 5 and x.shape[1] > 1 and x.stride(1) == 1) else "seq"
+
+
+def range_phase_c(src_joints, loc, wavelength, mode):
+    """src_joints: (N,3,T,E,M) f32 tensor -> (d, theta) f32 tensors (N,T,E,M) via the C recipe."""
+    n, c, t, e, m = src_joints.shape
+    aos = src_joints.permute(0, 2, 3, 4, 1).contiguous().numpy()  # (N,T,E,M,3)
+    cnt = aos.size // 3
+    d = np.empty(cnt, np.float32)
+    th = np.empty(cnt, np.float32)
+    locv = np.ascontiguousarray(np.asarray(loc, np.float32))
+    _lib().vr_oracle_range_phase(aos.ctypes.data, cnt, locv.ctypes.data,
+                                 ctypes.c_float(float(np.float32(wavelength))),
+                                 0 if mode == "seq" else 1, d.ctypes.data, th.ctypes.data)
+    shape = (n, t, e, m)
+    return torch.from_numpy(d.reshape(shape)), torch.from_numpy(th.reshape(shape))
+
+
+def bone_geometry(x, src, dst, loc, wavelength, distance="aten"):
+    """Per-bone range phase and RCS amplitude (layers/virtual_radar.py:93-119).
+
+    x (N,3,T,V,M); loc (3,) tensor; wavelength 0-d tensor.  Returns amp, phase, each (N,T,E,M).
+    """
+    S = x[:, :, :, src]                                   # :93  bone start joints
+    D = x[:, :, :, dst]                                   # :94  bone end joints
+    L = loc[:, None, None, None]
+    to_radar = torch.abs(S - L)                           # :96-98
+    if distance == "aten" or x.dtype != torch.float32:
+        rng = torch.norm(to_radar, dim=1)                 # :99  rounding-critical
+        phase = 4 * np.pi * rng / wavelength              # :119 rounding-critical
+    else:
+        rng, phase = range_phase_c(S, loc.detach().numpy(), float(wavelength), distance)
+    mid_to_radar = L - ((S + D) / 2)                      # :101-102  A
+    bone = D - S                                          # :103      B
+    cosang = torch.sum(mid_to_radar * bone, dim=1) / (
+        (torch.norm(mid_to_radar, dim=1) * torch.norm(bone, dim=1)) + 1e-6)
+    aspect = torch.acos(cosang)                           # :104-105
+    azim = torch.asin((loc[1] - S[:, 1]) /
+                      (torch.norm(to_radar[:, :2], dim=1) + 1e-6))   # :106-108
+    semi = torch.mean(torch.norm(S - D, dim=1), dim=2, keepdim=True)  # :110-112 mean over bones
+    semi = torch.pow(semi, 2)                             # :113
+    sin2 = torch.sin(aspect) ** 2
+    denom = (sin2 * (torch.cos(azim) ** 2) + sin2 * (torch.sin(azim) ** 2)
+             + semi * (torch.cos(aspect) ** 2))
+    rcs = (np.pi * semi) / denom ** 2                     # :114-116
+    return torch.sqrt(rcs), phase                         # :118
+
+
+def synthesize_iq(x, src, dst, loc, wavelength, distance="aten"):
+    """Complex baseband return summed over bones and bodies (:121-123) -> (N,T,2) [I,Q]."""
+    amp, phase = bone_geometry(x, src, dst, loc, wavelength, distance)
+    iq = torch.stack((amp * torch.cos(phase), amp * torch.sin(phase)), dim=4)
+    return torch.sum(iq, dim=[2, 3])
+
+
+def stft_logmag(iq, stft, n_fft):
+    """Two real STFTs combined into the complex one, log magnitude, fftshift (:124-133)."""
+    si = stft(iq[..., 0])
+    sq = stft(iq[..., 1])
+    z = torch.stack((si[..., 0] - sq[..., 1], si[..., 1] + sq[..., 0]), dim=-1)
+    mag = torch.norm(z, dim=-1)
+    return torch.roll(torch.log(mag + 1e-6), n_fft // 2, dims=1)
+
+
+class OracleVirtualRadar:
+    """Stateful convenience wrapper with the reference's constructor arguments."""
+
+    def __init__(self, edges=NTU_EDGES, wavelength=1e-3, radar_location=(0., 0., 0.),
+                 n_fft=256, hop_length=16, dtype=torch.float32):
+        self.src, self.dst = map(list, zip(*edges))
+        # parameters hold float32-rounded values in every variant (SURVEY 8c "truth-f64")
+        self.wavelength = torch.as_tensor(wavelength, dtype=torch.float32).to(dtype)
+        self.radar_location = torch.as_tensor(list(radar_location), dtype=torch.float32).to(dtype)
+        self.n_fft = n_fft
+        self.stft = STFT(n_fft=n_fft, freq_bins=n_fft, hop_length=hop_length,
+                         output_format="Complex", device="cpu")
+        if dtype != torch.float32:
+            self.stft = self.stft.to(dtype)
+            wsin, wcos = _f64_kernels(n_fft)
+            self.stft.wsin.data = wsin
+            self.stft.wcos.data = wcos
+        self.dtype = dtype
+
+    @torch.no_grad()
+    def iq(self, x, distance="aten"):
+        x = x if x.dtype == self.dtype else x.to(self.dtype)
+        return synthesize_iq(x, self.src, self.dst, self.radar_location, self.wavelength, distance)
+
+    @torch.no_grad()
+    def __call__(self, x, distance="aten"):
+        return stft_logmag(self.iq(x, distance), self.stft, self.n_fft)
+
+
+def _f64_kernels(n_fft):
+    from scipy.signal import get_window
+    s = np.arange(n_fft, dtype=np.float64)
+    k = np.arange(n_fft, dtype=np.float64)[:, None]
+    w = get_window("hann", n_fft, fftbins=True)
+    ang = 2 * np.pi * k * s / n_fft
+    return (torch.from_numpy((w * np.sin(ang))[:, None, :]),
+            torch.from_numpy((w * np.cos(ang))[:, None, :]))
+
+
+def forward(x, edges=NTU_EDGES, wavelength=1e-3, radar_location=(0., 0., 0.), n_fft=256,
+            hop_length=16, dtype=torch.float32, distance="aten"):
+    return OracleVirtualRadar(edges, wavelength, radar_location, n_fft, hop_length, dtype)(x, distance)
+
+
+# ---------------------------------------------------------------------------------------------
+# parity metric of SURVEY.md section 8d
+# ---------------------------------------------------------------------------------------------
+def parity_report(new, ref):
+    """Compare two log-spectrogram batches (N,n_fft,F).  Returns a dict of the tiered figures."""
+    new = np.asarray(new, np.float64)
+    ref = np.asarray(ref, np.float64)
+    lin_n = np.exp(new) - 1e-6
+    lin_r = np.exp(ref) - 1e-6
+    peak = lin_r.reshape(lin_r.shape[0], -1).max(axis=1)[:, None, None]
+    rel = np.abs(lin_n - lin_r) / np.maximum(np.abs(lin_r), 1e-300)
+    db = np.abs(new - ref) * (20.0 / np.log(10.0))
+    rep = {"global_abs_over_peak": float((np.abs(lin_n - lin_r) / peak).max()),
+           "nan_new": int(np.isnan(new).sum()), "nan_ref": int(np.isnan(ref).sum())}
+    for name, floor in (("t1", 1e-2), ("t2", 1e-4)):
+        sel = lin_r >= floor * peak
+        r, d = rel[sel], db[sel]
+        rep[name] = {"bins": int(sel.sum()),
+                     "rel_median": float(np.median(r)), "rel_p99": float(np.quantile(r, 0.99)),
+                     "rel_max": float(r.max()), "frac_rel_1e-4": float((r <= 1e-4).mean()),
+                     "db_max": float(d.max()), "frac_db_0.01": float((d <= 0.01).mean())}
+    return rep
+
+
+def parity_ok(rep):
+    """Pass/fail of the tiered criterion (tolerances stated in SURVEY.md 8d):
+    tier 1 (bins within 40 dB of the sample peak): rel err <= 1e-4 on >= 99.5 % and <= 0.01 dB on all;
+    tier 2 (within 80 dB): <= 0.01 dB on >= 99 %;  global: max |lin_new - lin_ref| / peak <= 5e-6."""
+    return (rep["nan_new"] == rep["nan_ref"]
+            and rep["t1"]["frac_rel_1e-4"] >= 0.995 and rep["t1"]["db_max"] <= 0.01
+            and rep["t2"]["frac_db_0.01"] >= 0.99
+            and rep["global_abs_over_peak"] <= 5e-6)

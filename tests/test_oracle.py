@@ -1,0 +1,132 @@
+"""CPU tests: the oracle port is pinned to the real reference's outputs (golden fixtures made by
+tests/golden/make_golden.py) and to BASELINE.md section 3's known answers."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import virtual_radar_oracle as vro
+from oracle.nnaudio_stft import STFT
+from tests import fixtures as fx
+from tests.conftest import GOLDEN, REFERENCE
+
+CASES = fx.golden_cases()
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_port_bit_equal_to_reference_golden(name):
+    x, kw, y, iq = CASES[name]
+    o = vro.OracleVirtualRadar(**kw)
+    assert np.array_equal(o.iq(x).numpy(), iq), "I/Q differs from the real reference"
+    got = o(x).numpy()
+    assert got.shape == y.shape
+    assert np.array_equal(got, y), "log-spectrogram differs from the real reference"
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_explicit_distance_recipe_equals_aten(name):
+    """The C recipe (mode from the strides) must reproduce torch.norm on THIS machine, so that
+    GPU parity tests, which use the explicit recipe, compare against the same numbers."""
+    x, kw, y, _ = CASES[name]
+    o = vro.OracleVirtualRadar(**kw)
+    mode = vro.distance_mode_for(x)
+    assert np.array_equal(o(x, distance=mode).numpy(), y)
+
+
+def test_distance_mode_rule():
+    x = torch.randn(2, 3, 140, 5, 2)
+    assert vro.distance_mode_for(x) == "seq"
+    nb = torch.randn(1, 140, 5, 1, 3).permute(0, 4, 1, 2, 3)
+    assert nb.stride(1) == 1 and vro.distance_mode_for(nb) == "fma"
+    assert vro.distance_mode_for(nb.contiguous()) == "seq"
+    assert vro.distance_mode_for(x[0].unsqueeze(0)) == "seq"
+
+
+def test_aten_norm_matches_c_recipe():
+    """Re-derive SURVEY fact 6 on the running machine: ATen's CPU norm over dim=1 is the 'seq'
+    recipe for strided coordinates and the 'fma' recipe for innermost coordinates."""
+    g = torch.Generator().manual_seed(3)
+    base = torch.randn(4, 300, 7, 2, 3, generator=g) * 0.7
+    loc = np.array([0.25, -0.5, 1.5], np.float32)
+    for mode, x in (("seq", base.permute(0, 4, 1, 2, 3).contiguous()), ("fma", base.permute(0, 4, 1, 2, 3))):
+        assert vro.distance_mode_for(x) == mode
+        aten = torch.norm(torch.abs(x - torch.from_numpy(loc)[:, None, None, None]), dim=1)
+        d, th = vro.range_phase_c(x, loc, 5e-4, mode)
+        assert torch.equal(aten, d), mode
+        lam = torch.as_tensor(5e-4)
+        assert torch.equal(4 * np.pi * aten / lam, th), mode
+        other = "fma" if mode == "seq" else "seq"
+        d2, _ = vro.range_phase_c(x, loc, 5e-4, other)
+        assert not torch.equal(aten, d2)
+
+
+def test_stft_restatement_equals_torch_stft():
+    """nnAudio restatement == two-sided torch.stft of the complex signal."""
+    g = torch.Generator().manual_seed(5)
+    iq = torch.randn(3, 500, 2, generator=g)
+    st = STFT(n_fft=256, freq_bins=256, hop_length=16, output_format="Complex", device="cpu")
+    got = vro.stft_logmag(iq, st, 256)
+    z = torch.complex(iq[..., 0].double(), iq[..., 1].double())
+    ref = torch.stft(z, 256, 16, window=torch.hann_window(256, periodic=True, dtype=torch.float64),
+                     center=True, pad_mode="reflect", onesided=False, return_complex=True)
+    ref = torch.roll(torch.log(ref.abs() + 1e-6), 128, dims=1)
+    assert got.shape == (3, 256, 500 // 16 + 1)
+    assert torch.allclose(got.double(), ref, atol=2e-4)
+    assert st.wsin.shape == (256, 1, 256) and st.wcos.shape == (256, 1, 256)
+
+
+def test_known_answers_small():
+    """BASELINE.md section 3 row A shape/min + notebook pin ln(1e-6) = -13.815511."""
+    ka = json.load(open(os.path.join(GOLDEN, "known_answers.json")))
+    assert ka["A"]["shape"] == [4, 256, 19]
+    assert abs(ka["A"]["min"] - np.log(np.float32(1e-6))) < 1e-5
+    assert abs(ka["A"]["sum"] - (-3473.635414)) < 1e-3 * 3473
+    assert ka["B"]["shape"] == [1, 256, 10313] and ka["C"]["shape"] == [1, 256, 3439]
+    assert ka["D"]["shape"] == [1, 256, 5121]
+    for k, mx in (("A", 6.0348787), ("B", 8.8132925), ("C", 7.5859632), ("D", 7.7540369), ("E", 6.3305459)):
+        assert abs(ka[k]["max"] - mx) < 1e-5
+
+
+def test_known_answer_E_full():
+    """Row E (seeded randn, N=256) recomputed by the port: exact argmax / 1e-3 relative sum."""
+    y = vro.forward(fx.s1_iid(256), wavelength=5e-4).numpy()
+    ka = json.load(open(os.path.join(GOLDEN, "known_answers.json")))["E"]
+    assert list(y.shape) == ka["shape"]
+    assert abs(y.astype(np.float64).sum() - ka["sum"]) <= 1e-9 * abs(ka["sum"])
+    assert [int(i) for i in np.unravel_index(np.argmax(y), y.shape)] == ka["argmax"]
+    assert y.max() == np.float32(ka["max"]) and y.min() == np.float32(ka["min"])
+
+
+@pytest.mark.skipif(not os.path.exists(REFERENCE), reason="reference data only in the build container")
+def test_known_answer_notebook_shapes_full():
+    """Notebook cells 3 (gait): printed shape (256, 5121) and BASELINE row D statistics."""
+    from oracle.pad_frames import pad_frames, notebook_tensor
+    gait = np.load(os.path.join(REFERENCE, "data", "simulated_gait.npy"))
+    x = notebook_tensor(pad_frames(gait, num_pad_frames=10))
+    assert tuple(x.stride()) == (3, 1, 51, 3, 3)
+    z = fx.load("gait_crop.npz")
+    y = vro.forward(x, edges=[tuple(e) for e in z["edges"].tolist()], wavelength=5e-4).numpy()
+    ka = json.load(open(os.path.join(GOLDEN, "known_answers.json")))["D"]
+    assert list(y.shape) == ka["shape"] == [1, 256, 5121]
+    assert y.max() == np.float32(ka["max"]) and y.min() == np.float32(ka["min"])
+    assert abs(y.astype(np.float64).sum() - ka["sum"]) <= 1e-9 * abs(ka["sum"])
+
+
+def test_truth_f64_close_to_f32_on_strong_bins():
+    x = fx.s3_smooth(2)
+    y32 = vro.forward(x, wavelength=5e-4)
+    y64 = vro.forward(x, wavelength=5e-4, dtype=torch.float64)
+    rep = vro.parity_report(y32.numpy(), y64.numpy())
+    assert rep["t1"]["rel_median"] < 5e-3     # f32 reference vs truth: SURVEY Appendix C scale
+    assert rep["nan_new"] == 0 and rep["nan_ref"] == 0
+
+
+def test_parity_metric_self():
+    y = vro.forward(fx.s1_iid(2), wavelength=5e-4).numpy()
+    rep = vro.parity_report(y, y)
+    assert vro.parity_ok(rep) and rep["t1"]["rel_max"] == 0.0
+    bad = y.copy()
+    bad[:, 100:110] += 0.01
+    assert not vro.parity_ok(vro.parity_report(bad, y))
