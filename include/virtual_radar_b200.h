@@ -1,0 +1,102 @@
+/* virtual_radar_b200.h -- C ABI of the B200-native VirtualRadar hot path.
+ *
+ * The reference (itskalvik/skeleton-action-recognition) is pure Python/PyTorch and has no FFI of
+ * its own; this header is the boundary a maintainer would bind (ctypes stub in INTEGRATION.md) to
+ * replace the body of `VirtualRadar.forward` (reference layers/virtual_radar.py:79-134) and the
+ * nnAudio `STFT` it constructs (layers/virtual_radar.py:71-76, called at :124-125).
+ *
+ * Conventions
+ *   - plain C, no torch types; all `*_dev` pointers are device pointers on the CURRENT CUDA device,
+ *     all `*_host` pointers are host pointers.  The caller owns every buffer.
+ *   - x      : (N, 3, T, V, M) float32, standard-contiguous  -- the layer's input layout
+ *              (layers/virtual_radar.py:82-83 docstring; produced by data_gen/gen_joint_data.py).
+ *   - out    : (N, n_fft, T / hop + 1) float32, contiguous   -- layers/virtual_radar.py:131-134.
+ *   - edges  : E bones as (src[e], dst[e]) joint indices, HOST arrays (the reference keeps them as
+ *              Python lists `self.src`, `self.dst`, layers/virtual_radar.py:70).
+ *   - wavelength_dev (1 float), radar_loc_dev (3 floats): the layer's two nn.Parameters
+ *              (layers/virtual_radar.py:65-69) read on the device, so no host sync is needed.
+ *   - every entry point returns 0 or a negative VR_ERR_* code; vr_last_error() gives the message
+ *     for the calling thread.  Nothing throws, exits, or synchronises the device, and work is
+ *     only enqueued on `stream` (a cudaStream_t passed as void*).
+ *   - re-entrant: no global mutable state except a per-thread error string and a per-device
+ *     one-time kernel attribute setup.
+ */
+#ifndef VIRTUAL_RADAR_B200_H
+#define VIRTUAL_RADAR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VR_ABI_VERSION 1
+
+#define VR_OK               0
+#define VR_ERR_ARG         -1   /* null pointer, bad flag                       (ValueError)   */
+#define VR_ERR_SHAPE       -2   /* T <= n_fft/2, edge index >= V, N/T/V/M <= 0   (ValueError)   */
+#define VR_ERR_UNSUPPORTED -3   /* shape outside what the kernels cover          (NotImplementedError) */
+#define VR_ERR_CUDA        -4   /* CUDA runtime error                            (RuntimeError) */
+
+/* flags */
+#define VR_FLAG_RANGE_FMA  1u   /* round the radar->joint range like ATen does when the caller's
+                                   tensor had the coordinate axis innermost (x.stride(1)==1):
+                                   sqrt(fma(c,c,fma(b,b,a*a))) instead of sqrt((a*a+b*b)+c*c).
+                                   Replaces torch.norm(dim=1) at layers/virtual_radar.py:99.      */
+
+int         vr_abi_version(void);
+const char* vr_last_error(void);
+
+/* The whole layer in one fused launch: geometry + RCS + baseband synthesis + windowed 256-point
+ * STFT + log magnitude + fftshift.  Replaces VirtualRadar.forward, layers/virtual_radar.py:79-134.
+ * n_fft must be 256 in this ABI version (the reference default, layers/virtual_radar.py:43).      */
+int vr_forward_f32(const float* x_dev, int64_t N, int64_t T, int32_t V, int32_t M,
+                   const int32_t* src_host, const int32_t* dst_host, int32_t E,
+                   const float* wavelength_dev, const float* radar_loc_dev,
+                   int32_t n_fft, int32_t hop, uint32_t flags,
+                   float* out_dev, void* stream);
+
+/* Same launch, additionally writing the intermediate complex baseband signal
+ * (N, T, 2) = [I, Q] -- `phase_data` after the sum at layers/virtual_radar.py:123 -- for stage-level
+ * parity tests.  The product path never materialises it.                                           */
+int vr_forward_debug_f32(const float* x_dev, int64_t N, int64_t T, int32_t V, int32_t M,
+                         const int32_t* src_host, const int32_t* dst_host, int32_t E,
+                         const float* wavelength_dev, const float* radar_loc_dev,
+                         int32_t n_fft, int32_t hop, uint32_t flags,
+                         float* out_dev, float* iq_dev, void* stream);
+
+/* End-to-end entry with HOST buffers (x_host pinned for full speed): splits the batch into
+ * sub-batches and pipelines H2D copy / fused kernel / D2H copy on two internal streams of the
+ * current device.  Blocks until out_host is complete.  Staging buffers are owned by the library,
+ * cached per device, and released by vr_release_host_staging().                                    */
+int vr_forward_host_f32(const float* x_host, int64_t N, int64_t T, int32_t V, int32_t M,
+                        const int32_t* src_host, const int32_t* dst_host, int32_t E,
+                        float wavelength, const float* radar_loc_host,
+                        int32_t n_fft, int32_t hop, uint32_t flags,
+                        float* out_host, int64_t sub_batch);
+int vr_release_host_staging(void);
+
+/* Host-side planning, callable without a GPU (used by tests and by bench.py's reporting).
+ * vr_plan fills `plan[16]`:
+ *   [0] grid  [1] block  [2] dynamic smem bytes  [3] ring stages  [4] frames per job
+ *   [5] jobs per sequence  [6] frames per output sub-batch  [7] uses TMA loads (0/1)
+ *   [8] uses TMA bulk store (0/1)  [9] chunks per job  [10] max bones per lane group
+ *   [11] max source joints per lane group  [12] z buffer capacity (samples)
+ *   [13] CTAs per SM targeted [14] time steps per chunk  [15] lane groups                        */
+int vr_plan(int64_t N, int64_t T, int32_t V, int32_t M,
+            const int32_t* src_host, const int32_t* dst_host, int32_t E,
+            int32_t n_fft, int32_t hop, int32_t sm_count, int64_t plan[16]);
+
+/* Bone -> lane-group assignment used by the synthesis stage (4 groups; all bones sharing a source
+ * joint stay in one group so the range phase of that joint is evaluated once).  group_of_edge[E]. */
+int vr_partition_edges(const int32_t* src_host, const int32_t* dst_host, int32_t E, int32_t V,
+                       int32_t* group_of_edge);
+
+/* Benchmark/tuning knob (process-wide, 0 = library default): warps per CTA (<=12), CTAs per SM
+ * targeted (<=4), cap on TMA ring stages.  Not needed for normal use.                             */
+int vr_set_tuning(int warps, int ctas_per_sm, int stages);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIRTUAL_RADAR_B200_H */

@@ -1,0 +1,90 @@
+"""ctypes binding of include/virtual_radar_b200.h (libvirtual_radar_b200.so, built in-tree by
+__graft_entry__.build()).  There is deliberately no fallback: if the shared object is missing the
+import of the layer fails loudly."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libvirtual_radar_b200.so")
+
+VR_OK, VR_ERR_ARG, VR_ERR_SHAPE, VR_ERR_UNSUPPORTED, VR_ERR_CUDA = 0, -1, -2, -3, -4
+VR_FLAG_RANGE_FMA = 1
+ABI_VERSION = 1
+
+# every symbol include/virtual_radar_b200.h declares
+SYMBOLS = ("vr_abi_version", "vr_last_error", "vr_forward_f32", "vr_forward_debug_f32",
+           "vr_forward_host_f32", "vr_release_host_staging", "vr_plan", "vr_partition_edges",
+           "vr_set_tuning")
+
+_lib = None
+
+
+class VirtualRadarLibraryError(ImportError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise VirtualRadarLibraryError(
+            "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU or PyTorch fallback for VirtualRadar." % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    c_i32p = ctypes.POINTER(ctypes.c_int32)
+    vp, i64, i32, u32, f32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_uint32, ctypes.c_float
+    L.vr_abi_version.restype = ctypes.c_int
+    L.vr_last_error.restype = ctypes.c_char_p
+    common = [vp, i64, i64, i32, i32, c_i32p, c_i32p, i32]
+    L.vr_forward_f32.argtypes = common + [vp, vp, i32, i32, u32, vp, vp]
+    L.vr_forward_debug_f32.argtypes = common + [vp, vp, i32, i32, u32, vp, vp, vp]
+    L.vr_forward_host_f32.argtypes = common + [f32, ctypes.POINTER(f32), i32, i32, u32, vp, i64]
+    L.vr_plan.argtypes = [i64, i64, i32, i32, c_i32p, c_i32p, i32, i32, i32, i32, ctypes.POINTER(i64)]
+    L.vr_partition_edges.argtypes = [c_i32p, c_i32p, i32, i32, c_i32p]
+    L.vr_set_tuning.argtypes = [ctypes.c_int] * 3
+    for name in ("vr_forward_f32", "vr_forward_debug_f32", "vr_forward_host_f32", "vr_plan",
+                 "vr_partition_edges", "vr_set_tuning", "vr_release_host_staging"):
+        getattr(L, name).restype = ctypes.c_int
+    if L.vr_abi_version() != ABI_VERSION:
+        raise VirtualRadarLibraryError("ABI mismatch: library %d, binding %d" % (L.vr_abi_version(), ABI_VERSION))
+    _lib = L
+    return L
+
+
+def last_error():
+    return lib().vr_last_error().decode("utf-8", "replace")
+
+
+def check(rc):
+    """Map a VR_ERR_* code to the exception class the reference would raise in that situation."""
+    if rc == VR_OK:
+        return
+    msg = last_error()
+    if rc in (VR_ERR_ARG, VR_ERR_SHAPE):
+        raise ValueError(msg)
+    if rc == VR_ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise RuntimeError(msg)
+
+
+def i32_array(values):
+    arr = (ctypes.c_int32 * len(values))(*[int(v) for v in values])
+    return arr
+
+
+PLAN_FIELDS = ("grid", "block", "smem_bytes", "ring_stages", "frames_per_job", "jobs_per_seq",
+               "frames_per_tile", "tma_loads", "tma_bulk_store", "chunks_per_job", "max_bones_per_group",
+               "max_sources_per_group", "z_capacity", "ctas_per_sm", "chunk_steps", "lane_groups")
+
+
+def plan(N, T, V, M, src, dst, n_fft=256, hop=16, sm_count=148):
+    out = (ctypes.c_int64 * 16)()
+    check(lib().vr_plan(N, T, V, M, i32_array(src), i32_array(dst), len(src), n_fft, hop, sm_count, out))
+    return dict(zip(PLAN_FIELDS, [int(v) for v in out]))
+
+
+def partition_edges(src, dst, V):
+    out = (ctypes.c_int32 * len(src))()
+    check(lib().vr_partition_edges(i32_array(src), i32_array(dst), len(src), V, out))
+    return [int(v) for v in out]

@@ -1,0 +1,360 @@
+// vr_cabi.cu -- C ABI (include/virtual_radar_b200.h) over the fused sm_100a kernel.
+// Host logic only: argument checks mirroring the reference's failure modes, bone partitioning,
+// launch planning, and the pipelined host-buffer entry point.  No torch, no ATen.
+#include "../../include/virtual_radar_b200.h"
+#include "vr_kernels.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t e_ = (expr);                                                                \
+        if (e_ != cudaSuccess) return fail(VR_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+
+struct Tuning { int warps = 0, ctas_per_sm = 0, stages = 0; };
+Tuning g_tuning;
+
+// ---- bone partition -----------------------------------------------------------------------------
+// Bones are grouped by source joint (the range phase of a joint is shared by all bones that start
+// there, layers/virtual_radar.py:93,99), and the source joints are spread over the 4 lane groups
+// by longest-processing-time-first on an instruction-cost estimate.
+struct Partition {
+    int group_of_edge[vr::NG * vr::MAX_EG * 4];
+    std::vector<int> src_of[vr::NG];                  // source joints per group (sorted by out-degree desc)
+    std::vector<std::vector<int>> edges_of[vr::NG];   // per source: list of edge ids
+    int ne[vr::NG], ns[vr::NG];
+};
+
+int partition_edges(const int32_t* src, const int32_t* dst, int E, int V, Partition& P) {
+    if (!src || !dst) return fail(VR_ERR_ARG, "edge arrays must not be null");
+    if (E <= 0) return fail(VR_ERR_SHAPE, "need at least one edge, got E=%d", E);
+    if (E > vr::NG * vr::MAX_EG) return fail(VR_ERR_UNSUPPORTED, "E=%d exceeds the supported %d bones", E, vr::NG * vr::MAX_EG);
+    for (int e = 0; e < E; ++e)
+        if (src[e] < 0 || src[e] >= V || dst[e] < 0 || dst[e] >= V)
+            return fail(VR_ERR_SHAPE, "edge %d = (%d,%d) indexes a joint outside [0,%d) (IndexError in the reference, layers/virtual_radar.py:93-94)", e, src[e], dst[e], V);
+    std::vector<int> joints;                            // distinct sources, first-appearance order
+    std::vector<std::vector<int>> out;                  // edges per source
+    for (int e = 0; e < E; ++e) {
+        size_t i = 0;
+        for (; i < joints.size(); ++i) if (joints[i] == src[e]) break;
+        if (i == joints.size()) { joints.push_back(src[e]); out.emplace_back(); }
+        out[i].push_back(e);
+    }
+    std::vector<int> order(joints.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+    const int COST_J = 36, COST_E = 39;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return out[a].size() > out[b].size(); });
+    long load[vr::NG] = {0, 0, 0, 0};
+    for (int g = 0; g < vr::NG; ++g) { P.src_of[g].clear(); P.edges_of[g].clear(); P.ne[g] = P.ns[g] = 0; }
+    for (int i : order) {
+        int best = 0;
+        for (int g = 1; g < vr::NG; ++g) if (load[g] < load[best]) best = g;
+        load[best] += COST_J + COST_E * (long)out[i].size();
+        P.src_of[best].push_back(joints[i]);
+        P.edges_of[best].push_back(out[i]);
+        P.ne[best] += (int)out[i].size();
+        P.ns[best] += 1;
+        for (int e : out[i]) P.group_of_edge[e] = best;
+    }
+    for (int g = 0; g < vr::NG; ++g)
+        if (P.ne[g] > vr::MAX_EG || P.ns[g] > vr::MAX_SG)
+            return fail(VR_ERR_UNSUPPORTED, "bone group %d too large (%d bones, %d source joints; max %d/%d)", g, P.ne[g], P.ns[g], vr::MAX_EG, vr::MAX_SG);
+    return VR_OK;
+}
+
+// ---- launch plan --------------------------------------------------------------------------------
+int round_up(int v, int a) { return (v + a - 1) / a * a; }
+
+int make_plan(int64_t N, int64_t T, int V, int M, const int32_t* src, const int32_t* dst, int E,
+              int n_fft, int hop, int sm_count, bool x_aligned, vr::Params& p, int& grid, int& ctas_per_sm) {
+    if (N <= 0 || T <= 0 || V <= 0 || M <= 0) return fail(VR_ERR_SHAPE, "N, T, V, M must be positive (got %lld, %lld, %d, %d)", (long long)N, (long long)T, V, M);
+    if (hop <= 0) return fail(VR_ERR_SHAPE, "hop_length must be positive, got %d", hop);
+    if (n_fft != vr::NFFT) return fail(VR_ERR_UNSUPPORTED, "this ABI version implements n_fft=256 only (got %d)", n_fft);
+    if (T <= n_fft / 2)
+        return fail(VR_ERR_SHAPE, "T=%lld must exceed n_fft/2=%d: reflect padding needs it (the reference raises 'Padding size should be less than the corresponding input dimension')", (long long)T, n_fft / 2);
+    if (T > (1ll << 30)) return fail(VR_ERR_UNSUPPORTED, "T=%lld too long", (long long)T);
+    if ((int64_t)V * M * 4 > 65535) return fail(VR_ERR_UNSUPPORTED, "V*M=%lld too large", (long long)V * M);
+    Partition P;
+    int rc = partition_edges(src, dst, E, V, P);
+    if (rc) return rc;
+
+    memset(&p, 0, sizeof(p));
+    p.N = N; p.T = T; p.V = V; p.M = M; p.E = E; p.hop = hop; p.VM = V * M;
+    p.F = (int)(T / hop) + 1;
+    p.inv_E = 1.0f / (float)E;
+    p.plane_floats = vr::TL * p.VM;
+    p.stage_bytes = round_up(3 * p.plane_floats * 4, 128);
+    p.tma_in = (x_aligned && ((T * p.VM) % 4 == 0)) ? 1 : 0;
+
+    // tables
+    p.eg_max = p.sg_max = 0;
+    for (int g = 0; g < vr::NG; ++g) {
+        p.ne[g] = P.ne[g]; p.ns[g] = P.ns[g];
+        p.eg_max = std::max(p.eg_max, P.ne[g]);
+        p.sg_max = std::max(p.sg_max, P.ns[g]);
+        int ei = 0;
+        for (size_t s = 0; s < P.src_of[g].size(); ++s) {
+            const int eb = ei;
+            for (int e : P.edges_of[g][s]) {
+                p.etab[ei * vr::NG + g] = (uint32_t)(src[e] * M) | ((uint32_t)(dst[e] * M) << 16);
+                ++ei;
+            }
+            p.stab[s * vr::NG + g] = (uint32_t)(P.src_of[g][s] * M) | ((uint32_t)eb << 16) | ((uint32_t)ei << 24);
+        }
+    }
+
+    // jobs: frames per job bounded by the z buffer
+    const int ZCAP_MAX = 2304;
+    int fj_max = (ZCAP_MAX - vr::NFFT - 2 * vr::TL - 2) / hop + 1;
+    if (fj_max < 1) return fail(VR_ERR_UNSUPPORTED, "hop_length=%d too large", hop);
+    p.jobs_per_seq = (p.F + fj_max - 1) / fj_max;
+    p.FJ = (p.F + p.jobs_per_seq - 1) / p.jobs_per_seq;
+    p.jobs_per_seq = (p.F + p.FJ - 1) / p.FJ;
+    p.n_jobs = N * (long long)p.jobs_per_seq;
+    int zspan = 0, cmax = 0;
+    for (int j = 0; j < p.jobs_per_seq; ++j) {
+        vr::JobGeom g = vr::job_geom(j, p.jobs_per_seq, p.FJ, p.F, hop, (int)T);
+        zspan = std::max(zspan, g.hi - g.lo + 1);
+        cmax = std::max(cmax, g.nchunks);
+    }
+    p.zcap = round_up(zspan, 16);
+    p.cmax = cmax;
+
+    // output tile
+    const int FB_BULK_MAX = 20;
+    if (p.jobs_per_seq == 1 && p.F <= FB_BULK_MAX) { p.FB = p.F; p.ostride = p.F; p.bulk_out = 1; }
+    else { p.FB = 16; p.ostride = 17; p.bulk_out = 0; }
+
+    // warps / CTAs per SM / ring depth
+    int W = g_tuning.warps > 0 ? g_tuning.warps : 8;
+    W = std::min(W, vr::MAX_WARPS);
+    p.W = W;
+    p.scr_bytes = round_up(std::max(vr::XCH_BYTES, p.eg_max * 128), 128);
+    int off = 0;
+    off += round_up(2 * vr::MAX_WARPS * 8, 128);                        // mbarriers (S <= 2*MAX_WARPS)
+    p.off_tab = off; off += (vr::NG * vr::MAX_EG + vr::NG * vr::MAX_SG) * 4;
+    p.off_tw = off;  off += vr::NFFT * 8;
+    p.off_z = off;   off += round_up(p.zcap * 8, 128);
+    p.off_o = off;   off += round_up(vr::NFFT * p.ostride * 4, 128);
+    p.off_scr = off; off += W * p.scr_bytes;
+    p.off_ring = off;
+    const int SMEM_SM = 233472, SMEM_CTA_MAX = 232448;
+    ctas_per_sm = g_tuning.ctas_per_sm > 0 ? g_tuning.ctas_per_sm : 2;
+    int S = 0;
+    for (; ctas_per_sm >= 1; --ctas_per_sm) {
+        int budget = std::min(SMEM_SM / ctas_per_sm - 1024, SMEM_CTA_MAX);
+        S = (budget - off) / p.stage_bytes;
+        S = std::min(S, 2 * W);
+        if (g_tuning.stages > 0) S = std::min(S, g_tuning.stages);
+        if (S >= std::min(4, 2 * W) || (ctas_per_sm == 1 && S >= 2)) break;
+    }
+    if (ctas_per_sm < 1 || S < 2)
+        return fail(VR_ERR_UNSUPPORTED, "V*M=%d needs %d-byte chunks; no room for a load ring in shared memory", p.VM, p.stage_bytes);
+    p.S = S;
+    p.smem_bytes = off + S * p.stage_bytes;
+    long long slots = (long long)sm_count * ctas_per_sm;
+    grid = (int)std::min<long long>(p.n_jobs, slots);
+    return VR_OK;
+}
+
+struct DeviceInfo { int sm_count = 0; bool attr_set = false; };
+std::mutex g_mu;
+DeviceInfo g_dev[64];
+
+int device_setup(int& dev, int& sm_count) {
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(VR_ERR_CUDA, "device index %d out of range", dev);
+    std::lock_guard<std::mutex> lk(g_mu);
+    DeviceInfo& d = g_dev[dev];
+    if (!d.attr_set) {
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+        if (prop.major < 10)
+            return fail(VR_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", dev, prop.major, prop.minor);
+        d.sm_count = prop.multiProcessorCount;
+        CUDA_TRY(cudaFuncSetAttribute(vr::vr_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        CUDA_TRY(cudaFuncSetAttribute(vr::vr_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        d.attr_set = true;
+    }
+    sm_count = d.sm_count;
+    return VR_OK;
+}
+
+int launch(const float* x, int64_t N, int64_t T, int V, int M, const int32_t* src, const int32_t* dst, int E,
+           const float* lam_dev, const float* loc_dev, float lam_val, const float* loc_val,
+           int n_fft, int hop, uint32_t flags, float* out, float* iq, cudaStream_t stream) {
+    if (!x || !out) return fail(VR_ERR_ARG, "x and out must not be null");
+    if ((lam_dev == nullptr) != (loc_dev == nullptr)) return fail(VR_ERR_ARG, "wavelength and radar_location must both be device pointers or both be null");
+    if (flags & ~VR_FLAG_RANGE_FMA) return fail(VR_ERR_ARG, "unknown flags 0x%x", flags);
+    int dev, sm_count;
+    int rc = device_setup(dev, sm_count);
+    if (rc) return rc;
+    vr::Params p;
+    int grid, cps;
+    rc = make_plan(N, T, V, M, src, dst, E, n_fft, hop, sm_count, ((uintptr_t)x & 15) == 0, p, grid, cps);
+    if (rc) return rc;
+    p.x = x; p.out = out; p.iq = iq;
+    p.lam_ptr = lam_dev; p.loc_ptr = loc_dev;
+    p.lam_val = lam_val;
+    if (loc_val) { p.loc_val[0] = loc_val[0]; p.loc_val[1] = loc_val[1]; p.loc_val[2] = loc_val[2]; }
+    if (flags & VR_FLAG_RANGE_FMA)
+        vr::vr_fused_kernel<true><<<grid, p.W * 32, p.smem_bytes, stream>>>(p);
+    else
+        vr::vr_fused_kernel<false><<<grid, p.W * 32, p.smem_bytes, stream>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    return VR_OK;
+}
+
+// ---- host staging for vr_forward_host_f32 ---------------------------------------------------------
+struct Staging {
+    float* x[2] = {nullptr, nullptr};
+    float* o[2] = {nullptr, nullptr};
+    size_t xcap = 0, ocap = 0;
+    cudaStream_t st[2] = {nullptr, nullptr};
+};
+Staging g_stage[64];
+std::mutex g_stage_mu;
+
+}  // namespace
+
+extern "C" {
+
+int vr_abi_version(void) { return VR_ABI_VERSION; }
+const char* vr_last_error(void) { return g_err; }
+
+int vr_set_tuning(int warps, int ctas_per_sm, int stages) {
+    if (warps < 0 || warps > vr::MAX_WARPS || ctas_per_sm < 0 || ctas_per_sm > 4 || stages < 0)
+        return fail(VR_ERR_ARG, "bad tuning (%d,%d,%d)", warps, ctas_per_sm, stages);
+    g_tuning.warps = warps; g_tuning.ctas_per_sm = ctas_per_sm; g_tuning.stages = stages;
+    return VR_OK;
+}
+
+int vr_forward_f32(const float* x_dev, int64_t N, int64_t T, int32_t V, int32_t M,
+                   const int32_t* src_host, const int32_t* dst_host, int32_t E,
+                   const float* wavelength_dev, const float* radar_loc_dev,
+                   int32_t n_fft, int32_t hop, uint32_t flags, float* out_dev, void* stream) {
+    if (!wavelength_dev || !radar_loc_dev) return fail(VR_ERR_ARG, "wavelength_dev and radar_loc_dev must not be null");
+    return launch(x_dev, N, T, V, M, src_host, dst_host, E, wavelength_dev, radar_loc_dev, 0.f, nullptr,
+                  n_fft, hop, flags, out_dev, nullptr, (cudaStream_t)stream);
+}
+
+int vr_forward_debug_f32(const float* x_dev, int64_t N, int64_t T, int32_t V, int32_t M,
+                         const int32_t* src_host, const int32_t* dst_host, int32_t E,
+                         const float* wavelength_dev, const float* radar_loc_dev,
+                         int32_t n_fft, int32_t hop, uint32_t flags, float* out_dev, float* iq_dev, void* stream) {
+    if (!wavelength_dev || !radar_loc_dev) return fail(VR_ERR_ARG, "wavelength_dev and radar_loc_dev must not be null");
+    if (!iq_dev) return fail(VR_ERR_ARG, "iq_dev must not be null");
+    return launch(x_dev, N, T, V, M, src_host, dst_host, E, wavelength_dev, radar_loc_dev, 0.f, nullptr,
+                  n_fft, hop, flags, out_dev, iq_dev, (cudaStream_t)stream);
+}
+
+int vr_forward_host_f32(const float* x_host, int64_t N, int64_t T, int32_t V, int32_t M,
+                        const int32_t* src_host, const int32_t* dst_host, int32_t E,
+                        float wavelength, const float* radar_loc_host,
+                        int32_t n_fft, int32_t hop, uint32_t flags, float* out_host, int64_t sub_batch) {
+    if (!x_host || !out_host || !radar_loc_host) return fail(VR_ERR_ARG, "host pointers must not be null");
+    if (N <= 0 || T <= 0 || V <= 0 || M <= 0 || hop <= 0) return fail(VR_ERR_SHAPE, "N, T, V, M, hop must be positive");
+    int dev, sm_count;
+    int rc = device_setup(dev, sm_count);
+    if (rc) return rc;
+    const size_t xseq = (size_t)3 * T * V * M, oseq = (size_t)n_fft * (T / hop + 1);
+    if (sub_batch <= 0) {
+        // ~16 MB of input per sub-batch keeps both copy engines and the SMs busy
+        sub_batch = std::max<int64_t>(1, (int64_t)((16u << 20) / (xseq * 4)));
+        sub_batch = std::min<int64_t>(sub_batch, (N + 3) / 4 > 0 ? (N + 3) / 4 : 1);
+    }
+    sub_batch = std::min<int64_t>(sub_batch, N);
+    Staging& sg = g_stage[dev];
+    std::lock_guard<std::mutex> lk(g_stage_mu);   // one host-pipelined call per process at a time
+    if (!sg.st[0]) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&sg.st[0], cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&sg.st[1], cudaStreamNonBlocking));
+    }
+    if (sg.xcap < sub_batch * xseq || sg.ocap < sub_batch * oseq) {
+        for (int i = 0; i < 2; ++i) {
+            if (sg.x[i]) cudaFree(sg.x[i]);
+            if (sg.o[i]) cudaFree(sg.o[i]);
+            sg.x[i] = sg.o[i] = nullptr;
+        }
+        sg.xcap = sg.ocap = 0;
+        for (int i = 0; i < 2; ++i) {
+            CUDA_TRY(cudaMalloc(&sg.x[i], sub_batch * xseq * 4));
+            CUDA_TRY(cudaMalloc(&sg.o[i], sub_batch * oseq * 4));
+        }
+        sg.xcap = sub_batch * xseq; sg.ocap = sub_batch * oseq;
+    }
+    int b = 0;
+    for (int64_t n0 = 0; n0 < N; n0 += sub_batch, b ^= 1) {
+        const int64_t nb = std::min<int64_t>(sub_batch, N - n0);
+        CUDA_TRY(cudaMemcpyAsync(sg.x[b], x_host + n0 * xseq, nb * xseq * 4, cudaMemcpyHostToDevice, sg.st[b]));
+        rc = launch(sg.x[b], nb, T, V, M, src_host, dst_host, E, nullptr, nullptr, wavelength, radar_loc_host,
+                    n_fft, hop, flags, sg.o[b], nullptr, sg.st[b]);
+        if (rc) { cudaStreamSynchronize(sg.st[0]); cudaStreamSynchronize(sg.st[1]); return rc; }
+        CUDA_TRY(cudaMemcpyAsync(out_host + n0 * oseq, sg.o[b], nb * oseq * 4, cudaMemcpyDeviceToHost, sg.st[b]));
+    }
+    CUDA_TRY(cudaStreamSynchronize(sg.st[0]));
+    CUDA_TRY(cudaStreamSynchronize(sg.st[1]));
+    return VR_OK;
+}
+
+int vr_release_host_staging(void) {
+    std::lock_guard<std::mutex> lk(g_stage_mu);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (int d = 0; d < 64; ++d) {
+        Staging& sg = g_stage[d];
+        if (!sg.st[0] && !sg.x[0]) continue;
+        cudaSetDevice(d);
+        for (int i = 0; i < 2; ++i) {
+            if (sg.x[i]) cudaFree(sg.x[i]);
+            if (sg.o[i]) cudaFree(sg.o[i]);
+            if (sg.st[i]) cudaStreamDestroy(sg.st[i]);
+            sg.x[i] = sg.o[i] = nullptr; sg.st[i] = nullptr;
+        }
+        sg.xcap = sg.ocap = 0;
+    }
+    cudaSetDevice(cur);
+    return VR_OK;
+}
+
+int vr_plan(int64_t N, int64_t T, int32_t V, int32_t M, const int32_t* src_host, const int32_t* dst_host,
+            int32_t E, int32_t n_fft, int32_t hop, int32_t sm_count, int64_t plan[16]) {
+    if (!plan) return fail(VR_ERR_ARG, "plan must not be null");
+    vr::Params p;
+    int grid, cps;
+    int rc = make_plan(N, T, V, M, src_host, dst_host, E, n_fft, hop, sm_count > 0 ? sm_count : 148, true, p, grid, cps);
+    if (rc) return rc;
+    plan[0] = grid; plan[1] = p.W * 32; plan[2] = p.smem_bytes; plan[3] = p.S; plan[4] = p.FJ;
+    plan[5] = p.jobs_per_seq; plan[6] = p.FB; plan[7] = p.tma_in; plan[8] = p.bulk_out; plan[9] = p.cmax;
+    plan[10] = p.eg_max; plan[11] = p.sg_max; plan[12] = p.zcap; plan[13] = cps; plan[14] = vr::TL; plan[15] = vr::NG;
+    return VR_OK;
+}
+
+int vr_partition_edges(const int32_t* src_host, const int32_t* dst_host, int32_t E, int32_t V, int32_t* group_of_edge) {
+    if (!group_of_edge) return fail(VR_ERR_ARG, "group_of_edge must not be null");
+    Partition P;
+    int rc = partition_edges(src_host, dst_host, E, V, P);
+    if (rc) return rc;
+    for (int e = 0; e < E; ++e) group_of_edge[e] = P.group_of_edge[e];
+    return VR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,182 @@
+"""Drop-in replacement for the reference's `layers/virtual_radar.py` (class `VirtualRadar`,
+module-level `edges`): same constructor arguments, same `forward(x)` signature, same
+`state_dict` keys -- but `forward` is one fused sm_100a CUDA kernel reached through the C ABI of
+include/virtual_radar_b200.h.  PyTorch is used only for device memory and streams.
+
+Reference behaviour mirrored here (file:line in /root/reference):
+  * constructor kwargs and defaults                     layers/virtual_radar.py:36-45
+  * parameters `wavelength` (0-d), `radar_location` (3,) layers/virtual_radar.py:65-69
+  * `self.src`, `self.dst` python lists                  layers/virtual_radar.py:70
+  * `self.stft` with parameters wsin/wcos (n_fft,1,n_fft) layers/virtual_radar.py:71-76 (nnAudio)
+  * forward: (N,3,T,V,M) f32 -> (N, n_fft, T//hop+1) f32  layers/virtual_radar.py:79-134
+
+There is no CPU path and no PyTorch fallback: a CPU tensor, a missing shared object or a shape the
+kernels do not cover raises.
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from .. import _cabi
+
+# Default skeleton: the reference's NTU RGB+D bone list (layers/virtual_radar.py:10-13),
+# grouped here by limb.  24 bones, 25 joints, 18 distinct source joints.
+_SPINE = [(0, 1), (1, 20), (20, 2), (2, 3)]
+_LEFT_ARM = [(20, 4), (4, 5), (5, 6), (6, 7), (7, 21), (7, 22)]
+_RIGHT_ARM = [(20, 8), (8, 9), (9, 10), (10, 11), (11, 23), (11, 24)]
+_HIPS = [(0, 16), (0, 12)]
+_LEFT_LEG = [(12, 13), (13, 14), (14, 15)]
+_RIGHT_LEG = [(16, 17), (17, 18), (18, 19)]
+edges = _SPINE + _LEFT_ARM + _RIGHT_ARM + _HIPS + _LEFT_LEG + _RIGHT_LEG
+
+
+class _STFTKernels(torch.nn.Module):
+    """Holds `wsin` / `wcos` so that `state_dict()` has the reference's `stft.wsin`, `stft.wcos`
+    entries (nnAudio 0.1.x STFT parameters).  The CUDA path evaluates the
+    same windowed DFT with an FFT and does not read these tensors; `assert_dft()` verifies that a
+    loaded checkpoint still holds the analytic Hann-windowed Fourier kernels."""
+
+    def __init__(self, n_fft, hop_length, trainable, device):
+        super().__init__()
+        self.n_fft, self.stride = n_fft, hop_length
+        wsin, wcos = self.analytic(n_fft)
+        self.wsin = torch.nn.Parameter(wsin.to(device), requires_grad=trainable)
+        self.wcos = torch.nn.Parameter(wcos.to(device), requires_grad=trainable)
+
+    @staticmethod
+    def analytic(n_fft):
+        s = np.arange(n_fft, dtype=np.float64)
+        window = 0.5 - 0.5 * np.cos(2 * np.pi * s / n_fft)          # scipy get_window('hann', fftbins=True)
+        ang = 2 * np.pi * np.arange(n_fft, dtype=np.float64)[:, None] * s[None, :] / n_fft
+        wsin = (window * np.sin(ang)).astype(np.float32)[:, None, :]
+        wcos = (window * np.cos(ang)).astype(np.float32)[:, None, :]
+        return torch.from_numpy(wsin), torch.from_numpy(wcos)
+
+    def assert_dft(self):
+        wsin, wcos = self.analytic(self.n_fft)
+        if not (torch.allclose(self.wsin.detach().cpu(), wsin, atol=1e-6)
+                and torch.allclose(self.wcos.detach().cpu(), wcos, atol=1e-6)):
+            raise NotImplementedError("stft.wsin/wcos differ from the Hann-windowed Fourier kernels; "
+                                      "trained STFT kernels are not supported by the CUDA path")
+
+
+class VirtualRadar(torch.nn.Module):
+    """Skeleton sequences -> micro-Doppler log-spectrograms on a B200 (see module docstring)."""
+
+    def __init__(self, edges=edges, wavelength=1e-3, radar_location=[0., 0., 0.],
+                 train_wavelength=False, train_radar_location=False, train_stft_kernel=False,
+                 n_fft=256, hop_length=16, device='cuda:0'):
+        super().__init__()
+        if train_wavelength or train_radar_location or train_stft_kernel:
+            raise NotImplementedError("the CUDA VirtualRadar is forward-only (SURVEY 8b); the reference's "
+                                      "training script never enables these flags either (main_spectrogram.py:128-136)")
+        _cabi.lib()   # fail at construction time if the extension is missing
+        self.wavelength = torch.nn.Parameter(torch.as_tensor(wavelength, dtype=torch.float32),
+                                             requires_grad=False)
+        self.radar_location = torch.nn.Parameter(torch.as_tensor(radar_location, dtype=torch.float32),
+                                                 requires_grad=False)
+        self.src, self.dst = map(list, zip(*edges))
+        self.stft = _STFTKernels(n_fft, hop_length, False, device)
+        self.n_fft = n_fft
+        self.hop_length = hop_length
+        self._src_c = _cabi.i32_array(self.src)
+        self._dst_c = _cabi.i32_array(self.dst)
+
+    # the ctypes arrays are not picklable / deep-copyable (DataParallel.replicate copies __dict__)
+    def __getstate__(self):
+        d = self.__dict__.copy()
+        d.pop("_src_c", None)
+        d.pop("_dst_c", None)
+        return d
+
+    def __setstate__(self, d):
+        self.__dict__.update(d)
+        self._src_c = _cabi.i32_array(self.src)
+        self._dst_c = _cabi.i32_array(self.dst)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        super()._load_from_state_dict(*args, **kwargs)
+
+    def output_shape(self, x_shape):
+        return (x_shape[0], self.n_fft, x_shape[2] // self.hop_length + 1)
+
+    def _check_input(self, x):
+        if not isinstance(x, torch.Tensor) or x.dim() != 5 or x.shape[1] != 3:
+            raise ValueError("expected x of shape (batch, 3, timesteps, vertices, num_graphs), got %s"
+                             % (tuple(x.shape) if isinstance(x, torch.Tensor) else type(x),))
+        if x.dtype != torch.float32:
+            raise ValueError("VirtualRadar computes in float32 like the reference; got %s" % x.dtype)
+        if x.requires_grad and torch.is_grad_enabled():
+            raise NotImplementedError("the CUDA VirtualRadar is forward-only: x.requires_grad is not supported")
+
+    def _prepare(self, x):
+        """Pick the range rounding mode from the caller's strides BEFORE normalising the layout
+        (ATen's CPU norm rounds differently when the coordinate axis is innermost)."""
+        flags = _cabi.VR_FLAG_RANGE_FMA if x.stride(1) == 1 and x.shape[1] > 1 else 0
+        return x.contiguous(), flags
+
+    def forward(self, x):
+        self._check_input(x)
+        if not x.is_cuda:
+            raise RuntimeError("VirtualRadar (B200) has no CPU path: move x to a CUDA device, or call "
+                               "forward_host(x) to stream a pinned host batch through the GPU")
+        lam, loc = self.wavelength, self.radar_location
+        if lam.device != x.device or loc.device != x.device:
+            raise RuntimeError("module parameters are on %s but x is on %s; call .to(x.device)" % (lam.device, x.device))
+        xc, flags = self._prepare(x)
+        N, _, T, V, M = xc.shape
+        out = torch.empty(self.output_shape(xc.shape), dtype=torch.float32, device=x.device)
+        if N == 0:
+            return out
+        with torch.cuda.device(x.device):
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            rc = _cabi.lib().vr_forward_f32(xc.data_ptr(), N, T, V, M, self._src_c, self._dst_c, len(self.src),
+                                            lam.data_ptr(), loc.data_ptr(), self.n_fft, self.hop_length,
+                                            flags, out.data_ptr(), ctypes.c_void_p(stream))
+        _cabi.check(rc)
+        return out
+
+    def forward_debug(self, x):
+        """forward plus the intermediate complex baseband signal (N,T,2); for stage-level parity tests."""
+        self._check_input(x)
+        xc, flags = self._prepare(x)
+        N, _, T, V, M = xc.shape
+        out = torch.empty(self.output_shape(xc.shape), dtype=torch.float32, device=x.device)
+        iq = torch.empty((N, T, 2), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            rc = _cabi.lib().vr_forward_debug_f32(xc.data_ptr(), N, T, V, M, self._src_c, self._dst_c, len(self.src),
+                                                  self.wavelength.data_ptr(), self.radar_location.data_ptr(),
+                                                  self.n_fft, self.hop_length, flags, out.data_ptr(), iq.data_ptr(),
+                                                  ctypes.c_void_p(stream))
+        _cabi.check(rc)
+        return out, iq
+
+    def forward_host(self, x, out=None, sub_batch=0, device=None):
+        """End-to-end call on HOST tensors: x (N,3,T,V,M) float32 on the CPU (pinned for full copy
+        speed) -> log-spectrograms on the CPU.  Sub-batches are pipelined H2D / kernel / D2H inside
+        the C library (vr_forward_host_f32)."""
+        self._check_input(x)
+        if x.is_cuda:
+            raise ValueError("forward_host takes a CPU tensor; use forward() for CUDA tensors")
+        xc, flags = self._prepare(x)
+        N, _, T, V, M = xc.shape
+        if out is None:
+            out = torch.empty(self.output_shape(xc.shape), dtype=torch.float32, pin_memory=True)
+        if N == 0:
+            return out
+        dev = torch.device(device) if device is not None else self.wavelength.device
+        if dev.type != "cuda":
+            dev = torch.device("cuda", torch.cuda.current_device())
+        loc = (ctypes.c_float * 3)(*[float(v) for v in self.radar_location.detach().cpu().tolist()])
+        with torch.cuda.device(dev):
+            rc = _cabi.lib().vr_forward_host_f32(xc.data_ptr(), N, T, V, M, self._src_c, self._dst_c, len(self.src),
+                                                 ctypes.c_float(float(self.wavelength.detach().cpu())), loc,
+                                                 self.n_fft, self.hop_length, flags, out.data_ptr(), int(sub_batch))
+        _cabi.check(rc)
+        return out
+
+    def extra_repr(self):
+        return "bones=%d, n_fft=%d, hop_length=%d" % (len(self.src), self.n_fft, self.hop_length)

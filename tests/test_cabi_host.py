@@ -1,0 +1,119 @@
+"""CPU tests of the C-ABI library: it loads without a GPU, exports every symbol the header declares,
+and its host-side logic (planner, bone partitioner, argument checks) behaves."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from tests.conftest import ROOT
+
+
+@pytest.fixture(scope="module")
+def cabi():
+    import __graft_entry__ as ge
+    ge.build()
+    from skeleton_action_recognition_b200 import _cabi
+    return _cabi
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "virtual_radar_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(vr_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(cabi):
+    L = cabi.lib()
+    names = header_symbols()
+    assert set(names) == set(cabi.SYMBOLS), (names, cabi.SYMBOLS)
+    for n in names:
+        assert hasattr(L, n), n
+    assert L.vr_abi_version() == 1
+
+
+def test_plan_ntu(cabi):
+    from skeleton_action_recognition_b200 import edges
+    src, dst = map(list, zip(*edges))
+    p = cabi.plan(256, 300, 25, 2, src, dst)
+    assert p["frames_per_job"] == 19 and p["jobs_per_seq"] == 1 and p["grid"] == 256
+    assert p["tma_loads"] == 1 and p["tma_bulk_store"] == 1
+    assert p["chunks_per_job"] == 38 and p["chunk_steps"] == 8
+    assert p["smem_bytes"] <= 232448 // 2
+    assert p["max_bones_per_group"] == 6
+    p = cabi.plan(65536, 300, 25, 2, src, dst)
+    assert p["grid"] == 148 * p["ctas_per_sm"]
+    p = cabi.plan(1, 165000, 25, 1, src, dst)
+    assert p["jobs_per_seq"] * p["frames_per_job"] >= 10313 and p["tma_bulk_store"] == 0
+    assert p["z_capacity"] >= (p["frames_per_job"] - 1) * 16 + 256
+    p = cabi.plan(2, 301, 25, 1, src, dst)       # T*V*M not a multiple of 4 -> no TMA loads
+    assert p["tma_loads"] == 0
+
+
+def test_partition_keeps_sources_together_and_balances(cabi):
+    from skeleton_action_recognition_b200 import edges
+    src, dst = map(list, zip(*edges))
+    grp = cabi.partition_edges(src, dst, 25)
+    assert len(grp) == 24 and set(grp) <= {0, 1, 2, 3}
+    by_src = {}
+    for s, g in zip(src, grp):
+        by_src.setdefault(s, set()).add(g)
+    assert all(len(v) == 1 for v in by_src.values())
+    counts = [grp.count(g) for g in range(4)]
+    assert max(counts) == 6 and min(counts) == 6
+    chain = [(i, i + 1) for i in range(41)]
+    s2, d2 = map(list, zip(*chain))
+    g2 = cabi.partition_edges(s2, d2, 42)
+    assert sorted(g2.count(g) for g in range(4)) == [10, 10, 10, 11]
+    star = [(0, i) for i in range(1, 9)]
+    s3, d3 = map(list, zip(*star))
+    assert len(set(cabi.partition_edges(s3, d3, 9))) == 1
+
+
+def test_argument_errors(cabi):
+    from skeleton_action_recognition_b200 import edges
+    src, dst = map(list, zip(*edges))
+    with pytest.raises(ValueError, match="exceed n_fft/2"):
+        cabi.plan(1, 128, 25, 1, src, dst)
+    cabi.plan(1, 129, 25, 1, src, dst)
+    with pytest.raises(ValueError, match="outside"):
+        cabi.plan(1, 300, 24, 1, src, dst)          # joint 24 does not exist
+    with pytest.raises(NotImplementedError, match="n_fft=256"):
+        cabi.plan(1, 300, 25, 1, src, dst, n_fft=512)
+    with pytest.raises(ValueError):
+        cabi.plan(0, 300, 25, 1, src, dst)
+    with pytest.raises(ValueError):
+        cabi.plan(1, 300, 25, 1, src, dst, hop=0)
+
+
+def test_module_surface_matches_reference():
+    import torch
+    from skeleton_action_recognition_b200 import VirtualRadar, edges
+    assert len(edges) == 24 and edges[0] == (0, 1) and edges[-1] == (18, 19)
+    layer = VirtualRadar(wavelength=5e-4, device="cpu")
+    sd = layer.state_dict()
+    assert list(sd.keys()) == ["wavelength", "radar_location", "stft.wsin", "stft.wcos"]
+    assert sd["wavelength"].shape == () and sd["radar_location"].shape == (3,)
+    assert sd["stft.wsin"].shape == (256, 1, 256) and sd["stft.wcos"].shape == (256, 1, 256)
+    assert layer.src[:3] == [0, 1, 20] and layer.dst[:3] == [1, 20, 2] and layer.n_fft == 256
+    assert not any(p.requires_grad for p in layer.parameters())
+    # the STFT kernel parameters equal the oracle's nnAudio restatement bit for bit
+    from oracle.nnaudio_stft import fourier_kernels
+    wsin, wcos = fourier_kernels(256, 256)
+    assert torch.equal(sd["stft.wsin"], torch.from_numpy(wsin))
+    assert torch.equal(sd["stft.wcos"], torch.from_numpy(wcos))
+    layer.stft.assert_dft()
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        layer(torch.zeros(1, 3, 300, 25, 2))
+    with pytest.raises(ValueError):
+        layer(torch.zeros(1, 2, 300, 25, 2))
+    with pytest.raises(NotImplementedError):
+        VirtualRadar(train_wavelength=True, device="cpu")
+    import copy, pickle
+    c = copy.deepcopy(layer)
+    assert c.src == layer.src
+    pickle.loads(pickle.dumps(layer))
+    # reference-style checkpoints load
+    layer2 = VirtualRadar(wavelength=1e-3, device="cpu")
+    layer2.load_state_dict(sd)
+    assert float(layer2.wavelength) == float(layer.wavelength)

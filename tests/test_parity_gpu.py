@@ -1,0 +1,192 @@
+"""GPU parity tests: the fused CUDA path (through the C ABI) against the CPU oracle and the committed
+golden vectors of the real reference.  Tolerances are SURVEY 8d's tiered criterion, written out in
+oracle.virtual_radar_oracle.parity_ok:
+  tier 1 (bins within 40 dB of the sample peak): rel err on linear magnitude <= 1e-4 on >= 99.5 % of
+          bins and <= 0.01 dB on all;  tier 2 (within 80 dB): <= 0.01 dB on >= 99 %;
+  global: max |lin_new - lin_ref| / peak <= 5e-6.
+Nothing here reads /root/reference."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import virtual_radar_oracle as vro
+from tests import fixtures as fx
+
+pytestmark = pytest.mark.gpu
+
+REPORT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+
+
+def _layer(**kw):
+    from skeleton_action_recognition_b200 import VirtualRadar
+    return VirtualRadar(device="cuda:0", **kw).to("cuda:0")
+
+
+def _record(name, rep):
+    try:
+        os.makedirs(REPORT, exist_ok=True)
+        with open(os.path.join(REPORT, "parity_report.jsonl"), "a") as f:
+            f.write(json.dumps({"case": name, **rep}) + "\n")
+    except OSError:
+        pass
+
+
+def _iq_check(iq_gpu, iq_ref, tol=2e-5):
+    """Baseband samples: error relative to the per-sequence RMS magnitude."""
+    a = iq_gpu.astype(np.float64)
+    b = iq_ref.astype(np.float64)
+    rms = np.sqrt((b ** 2).sum(-1).mean(-1))[:, None, None] + 1e-30
+    err = np.abs(a - b) / rms
+    return float(err.max()), float(np.median(err))
+
+
+CASES = fx.golden_cases()
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_golden_vectors_of_the_real_reference(name):
+    x, kw, y, iq = CASES[name]
+    layer = _layer(**kw)
+    out, iq_gpu = layer.forward_debug(x.cuda())      # .cuda() preserves the notebook's strides
+    torch.cuda.synchronize()
+    assert tuple(out.shape) == y.shape
+    mx, med = _iq_check(iq_gpu.cpu().numpy(), iq)
+    rep = vro.parity_report(out.cpu().numpy(), y)
+    rep["iq_max_rel_rms"], rep["iq_median_rel_rms"] = mx, med
+    _record("golden/" + name, rep)
+    assert mx < 2e-5, (mx, med)
+    assert vro.parity_ok(rep), rep
+    # forward() and forward_debug() are the same launch
+    assert torch.equal(layer(x.cuda()), out)
+
+
+@pytest.mark.parametrize("maker,n", [(fx.s1_iid, 64), (fx.s2_ntu_like, 64), (fx.s3_smooth, 16)])
+def test_synthetic_inputs_vs_oracle(maker, n):
+    x = maker(n)
+    layer = _layer(wavelength=5e-4)
+    out = layer(x.cuda()).cpu().numpy()
+    ref = vro.forward(x, wavelength=5e-4, distance=vro.distance_mode_for(x)).numpy()
+    rep = vro.parity_report(out, ref)
+    _record("synthetic/" + maker.__name__, rep)
+    assert vro.parity_ok(rep), rep
+
+
+def test_layout_selects_range_rounding_mode():
+    """Same values, two layouts: the kernel must follow the reference's layout-dependent rounding."""
+    g = torch.Generator().manual_seed(11)
+    base = torch.randn(2, 400, 25, 1, 3, generator=g) * 0.5
+    x_fma = base.permute(0, 4, 1, 2, 3)                  # coordinate axis innermost
+    x_seq = x_fma.contiguous()
+    layer = _layer(wavelength=5e-4)
+    for x in (x_fma, x_seq):
+        mode = vro.distance_mode_for(x)
+        out = layer(x.cuda()).cpu().numpy()
+        ref = vro.forward(x, wavelength=5e-4, distance=mode).numpy()
+        rep = vro.parity_report(out, ref)
+        _record("layout/" + mode, rep)
+        assert vro.parity_ok(rep), (mode, rep)
+    a = layer(x_fma.cuda())
+    b = layer(x_seq.cuda())
+    assert not torch.equal(a, b)
+
+
+@pytest.mark.parametrize("shape,E", [((2, 3, 129, 5, 1), 4), ((3, 3, 130, 7, 3), 6), ((1, 3, 301, 25, 1), 24),
+                                     ((2, 3, 1000, 17, 2), 16), ((1, 3, 5000, 42, 1), 41), ((5, 3, 257, 3, 4), 2)])
+def test_odd_shapes(shape, E):
+    """T=129 (minimum), unaligned T*V*M (no TMA), M in {1,2,3,4}, chains, long sequences with several jobs."""
+    g = torch.Generator().manual_seed(shape[2])
+    x = torch.randn(*shape, generator=g) * 0.4
+    V = shape[3]
+    edges = [(i % V, (i * 3 + 1) % V) for i in range(E)]
+    edges = [(a, b if b != a else (a + 1) % V) for a, b in edges]
+    kw = dict(edges=edges, wavelength=2e-3, radar_location=[0.1, 0.2, -0.3])
+    out = _layer(**kw)(x.cuda()).cpu().numpy()
+    ref = vro.forward(x, distance="seq", **kw).numpy()
+    assert out.shape == ref.shape == (shape[0], 256, shape[2] // 16 + 1)
+    rep = vro.parity_report(out, ref)
+    _record("odd/%s" % (shape,), rep)
+    assert vro.parity_ok(rep), rep
+
+
+def test_hop_length_variants():
+    x = fx.s1_iid(3, seed=4, shape=(3, 700, 25, 2))
+    for hop in (8, 16, 32, 100):
+        out = _layer(wavelength=1e-3, hop_length=hop)(x.cuda()).cpu().numpy()
+        ref = vro.forward(x, wavelength=1e-3, hop_length=hop, distance="seq").numpy()
+        assert out.shape == ref.shape
+        assert vro.parity_ok(vro.parity_report(out, ref)), hop
+
+
+def test_zero_and_absent_bodies():
+    """All-zero sequences give ln(1e-6); an absent second body changes nothing (both occur in NTU)."""
+    layer = _layer(wavelength=5e-4)
+    z = torch.zeros(2, 3, 300, 25, 2)
+    out = layer(z.cuda()).cpu()
+    assert torch.allclose(out, torch.full_like(out, float(np.log(np.float32(1e-6)))), atol=1e-4)
+    x = fx.s1_iid(4)
+    x[:, :, :, :, 1] = 0
+    one = layer(x[..., :1].contiguous().cuda())
+    two = layer(x.cuda())
+    assert torch.equal(one, two)
+
+
+def test_full_size_properties_config2():
+    """BASELINE config 2 at full size (N=256): determinism, batch-slice consistency, and the
+    known-answer row E of BASELINE.md section 3 (sum to 1e-6 relative, min/max to 1e-4)."""
+    x = fx.s1_iid(256)
+    layer = _layer(wavelength=5e-4)
+    xg = x.cuda()
+    y = layer(xg)
+    assert torch.equal(y, layer(xg))
+    assert torch.equal(y[37:41], layer(xg[37:41]))
+    ka = json.load(open(os.path.join(fx.GOLDEN, "known_answers.json")))["E"]
+    yc = y.cpu().numpy()
+    assert list(yc.shape) == ka["shape"]
+    assert abs(yc.astype(np.float64).sum() - ka["sum"]) <= 1e-6 * abs(ka["sum"])
+    assert abs(yc.max() - ka["max"]) < 1e-4 and abs(yc.min() - ka["min"]) < 2e-3
+    assert [int(i) for i in np.unravel_index(np.argmax(yc), yc.shape)] == ka["argmax"]
+
+
+def test_large_batch_persistent_loop():
+    """More jobs than resident CTAs: every CTA loops over several jobs and the ring runs across them."""
+    x = fx.s1_iid(64)
+    big = x.repeat(40, 1, 1, 1, 1)                      # 2560 sequences
+    layer = _layer(wavelength=5e-4)
+    y = layer(big.cuda())
+    y0 = layer(x.cuda())
+    assert torch.equal(y, y0.repeat(40, 1, 1))
+
+
+def test_host_entry_matches_device_entry():
+    x = fx.s1_iid(96).pin_memory()
+    layer = _layer(wavelength=5e-4)
+    y_dev = layer(x.cuda()).cpu()
+    y_host = layer.forward_host(x, sub_batch=40)
+    assert torch.equal(y_dev, y_host)
+    y_host2 = layer.forward_host(x)
+    assert torch.equal(y_dev, y_host2)
+
+
+def test_stream_and_no_sync():
+    x = fx.s1_iid(8).cuda()
+    layer = _layer(wavelength=5e-4)
+    s = torch.cuda.Stream()
+    ref = layer(x)
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        y = layer(x)
+    s.synchronize()
+    assert torch.equal(y, ref)
+
+
+def test_errors_on_gpu_inputs():
+    layer = _layer(wavelength=5e-4)
+    with pytest.raises(ValueError, match="exceed n_fft/2"):
+        layer(torch.zeros(1, 3, 128, 25, 2, device="cuda"))
+    with pytest.raises(ValueError):
+        layer(torch.zeros(1, 3, 300, 25, 2, device="cuda", dtype=torch.float64))
+    with pytest.raises(ValueError, match="outside"):
+        layer(torch.zeros(1, 3, 300, 20, 2, device="cuda"))
