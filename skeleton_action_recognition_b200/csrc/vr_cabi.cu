@@ -149,7 +149,7 @@ int make_plan(int64_t N, int64_t T, int V, int M, const int32_t* src, const int3
     p.W = W;
     p.scr_bytes = round_up(std::max(vr::XCH_BYTES, p.eg_max * 128), 128);
     int off = 0;
-    off += round_up(2 * vr::MAX_WARPS * 8, 128);                        // mbarriers (S <= 2*MAX_WARPS)
+    off += round_up(2 * vr::MAX_WARPS * (8 + 4), 128);                  // mbarriers + issued sequence numbers (S <= 2*MAX_WARPS)
     p.off_tab = off; off += (vr::NG * vr::MAX_EG + vr::NG * vr::MAX_SG) * 4;
     p.off_tw = off;  off += vr::NFFT * 8;
     p.off_z = off;   off += round_up(p.zcap * 8, 128);

