@@ -62,6 +62,10 @@ def _lib():
                                               ctypes.c_float, ctypes.c_int, ctypes.c_void_p,
                                               ctypes.c_void_p]
         lib.vr_oracle_range_phase.restype = None
+        lib.vr_oracle_aspect_cosine.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                                ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                                ctypes.c_void_p]
+        lib.vr_oracle_aspect_cosine.restype = None
         _LIB = lib
     return _LIB
 
@@ -85,6 +89,20 @@ def range_phase_c(src_joints, loc, wavelength, mode):
                                  0 if mode == "seq" else 1, d.ctypes.data, th.ctypes.data)
     shape = (n, t, e, m)
     return torch.from_numpy(d.reshape(shape)), torch.from_numpy(th.reshape(shape))
+
+
+def aspect_cosine_c(src_joints, dst_joints, loc, mode):
+    """(N,3,T,E,M) f32 bone end points -> (u, bone length), each (N,T,E,M), via the C recipe."""
+    n, c, t, e, m = src_joints.shape
+    s = src_joints.permute(0, 2, 3, 4, 1).contiguous().numpy()
+    d = dst_joints.permute(0, 2, 3, 4, 1).contiguous().numpy()
+    cnt = s.size // 3
+    u = np.empty(cnt, np.float32)
+    ln = np.empty(cnt, np.float32)
+    locv = np.ascontiguousarray(np.asarray(loc, np.float32))
+    _lib().vr_oracle_aspect_cosine(s.ctypes.data, d.ctypes.data, cnt, locv.ctypes.data,
+                                   0 if mode == "seq" else 1, u.ctypes.data, ln.ctypes.data)
+    return torch.from_numpy(u.reshape(n, t, e, m)), torch.from_numpy(ln.reshape(n, t, e, m))
 
 
 def bone_geometry(x, src, dst, loc, wavelength, distance="aten"):

@@ -62,6 +62,22 @@ def test_aten_norm_matches_c_recipe():
         assert not torch.equal(aten, d2)
 
 
+def test_aten_aspect_cosine_matches_c_recipe():
+    """The bone aspect cosine u (amplified by 1/c in the RCS) as ATen rounds it in each layout ==
+    the C restatement the CUDA kernel follows: norms in the layout's mode, dot = (p0+p1)+p2."""
+    g = torch.Generator().manual_seed(9)
+    base = torch.randn(3, 200, 9, 2, 3, generator=g) * 0.6
+    loc = torch.tensor([0.3, -0.2, 1.1])
+    src, dst = list(range(8)), list(range(1, 9))
+    for mode, x in (("seq", base.permute(0, 4, 1, 2, 3).contiguous()), ("fma", base.permute(0, 4, 1, 2, 3))):
+        S, D, L = x[:, :, :, src], x[:, :, :, dst], loc[:, None, None, None]
+        A, B = L - ((S + D) / 2), D - S
+        u_aten = torch.sum(A * B, dim=1) / ((torch.norm(A, dim=1) * torch.norm(B, dim=1)) + 1e-6)
+        u_c, len_c = vro.aspect_cosine_c(S, D, loc.numpy(), mode)
+        assert torch.equal(u_aten, u_c), mode
+        assert torch.equal(torch.norm(S - D, dim=1), len_c), mode
+
+
 def test_stft_restatement_equals_torch_stft():
     """nnAudio restatement == two-sided torch.stft of the complex signal."""
     g = torch.Generator().manual_seed(5)
