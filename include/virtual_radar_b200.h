@@ -92,6 +92,11 @@ int vr_plan(int64_t N, int64_t T, int32_t V, int32_t M,
 int vr_partition_edges(const int32_t* src_host, const int32_t* dst_host, int32_t E, int32_t V,
                        int32_t* group_of_edge);
 
+/* GPU self-test (synchronous; test infrastructure): the kernels replace __fsqrt_rn/__fdiv_rn by their
+ * branch-free fast-path sequences; this counts bitwise mismatches against the intrinsics over n
+ * pseudo-random operands: [0] sqrt, [1] divide by `wavelength`, [2] general divide.               */
+int vr_selftest_rounding(uint64_t n, float wavelength, uint64_t mismatches[3]);
+
 /* Benchmark/tuning knob (process-wide, 0 = library default): warps per CTA (<=12), CTAs per SM
  * targeted (<=4), cap on TMA ring stages.  Not needed for normal use.                             */
 int vr_set_tuning(int warps, int ctas_per_sm, int stages);

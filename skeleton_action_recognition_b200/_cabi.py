@@ -14,7 +14,7 @@ ABI_VERSION = 1
 # every symbol include/virtual_radar_b200.h declares
 SYMBOLS = ("vr_abi_version", "vr_last_error", "vr_forward_f32", "vr_forward_debug_f32",
            "vr_forward_host_f32", "vr_release_host_staging", "vr_plan", "vr_partition_edges",
-           "vr_set_tuning")
+           "vr_set_tuning", "vr_selftest_rounding")
 
 _lib = None
 
@@ -43,6 +43,8 @@ def lib():
     L.vr_plan.argtypes = [i64, i64, i32, i32, c_i32p, c_i32p, i32, i32, i32, i32, ctypes.POINTER(i64)]
     L.vr_partition_edges.argtypes = [c_i32p, c_i32p, i32, i32, c_i32p]
     L.vr_set_tuning.argtypes = [ctypes.c_int] * 3
+    L.vr_selftest_rounding.argtypes = [ctypes.c_uint64, f32, ctypes.POINTER(ctypes.c_uint64)]
+    L.vr_selftest_rounding.restype = ctypes.c_int
     for name in ("vr_forward_f32", "vr_forward_debug_f32", "vr_forward_host_f32", "vr_plan",
                  "vr_partition_edges", "vr_set_tuning", "vr_release_host_staging"):
         getattr(L, name).restype = ctypes.c_int
@@ -82,6 +84,12 @@ def plan(N, T, V, M, src, dst, n_fft=256, hop=16, sm_count=148):
     out = (ctypes.c_int64 * 16)()
     check(lib().vr_plan(N, T, V, M, i32_array(src), i32_array(dst), len(src), n_fft, hop, sm_count, out))
     return dict(zip(PLAN_FIELDS, [int(v) for v in out]))
+
+
+def selftest_rounding(n, wavelength):
+    out = (ctypes.c_uint64 * 3)()
+    check(lib().vr_selftest_rounding(n, wavelength, out))
+    return [int(v) for v in out]
 
 
 def partition_edges(src, dst, V):

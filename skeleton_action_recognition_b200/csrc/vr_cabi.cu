@@ -114,11 +114,19 @@ int make_plan(int64_t N, int64_t T, int V, int M, const int32_t* src, const int3
         for (size_t s = 0; s < P.src_of[g].size(); ++s) {
             const int eb = ei;
             for (int e : P.edges_of[g][s]) {
-                p.etab[ei * vr::NG + g] = (uint32_t)(src[e] * M) | ((uint32_t)(dst[e] * M) << 16);
+                p.etab[ei * vr::NG + g] = (uint32_t)(src[e] * M * 4) | ((uint32_t)(dst[e] * M * 4) << 16);
                 ++ei;
             }
-            p.stab[s * vr::NG + g] = (uint32_t)(P.src_of[g][s] * M) | ((uint32_t)eb << 16) | ((uint32_t)ei << 24);
+            p.stab[s * vr::NG + g] = (uint32_t)(P.src_of[g][s] * M * 4) | ((uint32_t)eb << 16) | ((uint32_t)ei << 24);
         }
+    }
+    // padding entries: a zero-length bone (src == dst) on a joint that some real bone uses, so that
+    // it adds exactly 0 to the bone-length sum and can only be NaN if the reference's output is NaN;
+    // padding source joints carry an empty bone range and are masked in the kernel.
+    for (int g = 0; g < vr::NG; ++g) {
+        const uint32_t j = (uint32_t)((P.src_of[g].empty() ? src[0] : P.src_of[g][0]) * M * 4);
+        for (int ei = P.ne[g]; ei < p.eg_max; ++ei) p.etab[ei * vr::NG + g] = j | (j << 16);
+        for (int si = P.ns[g]; si < p.sg_max; ++si) p.stab[si * vr::NG + g] = j;
     }
 
     // jobs: frames per job bounded by the z buffer
@@ -175,6 +183,27 @@ int make_plan(int64_t N, int64_t T, int V, int M, const int32_t* src, const int3
     return VR_OK;
 }
 
+// kernel variants: range rounding mode x compile-time V*M (plane stride as an immediate); VM=0 is generic
+typedef void (*KernelFn)(const vr::Params);
+struct Variant { bool fma; int vm; KernelFn fn; };
+const Variant kVariants[] = {
+    {false, 0, vr::vr_fused_kernel<false, 0>},   {true, 0, vr::vr_fused_kernel<true, 0>},
+    {false, 50, vr::vr_fused_kernel<false, 50>}, {true, 50, vr::vr_fused_kernel<true, 50>},   // NTU, two bodies
+    {false, 25, vr::vr_fused_kernel<false, 25>}, {true, 25, vr::vr_fused_kernel<true, 25>},   // NTU, one body
+    {false, 17, vr::vr_fused_kernel<false, 17>}, {true, 17, vr::vr_fused_kernel<true, 17>},   // simulated gait
+    {false, 42, vr::vr_fused_kernel<false, 42>}, {true, 42, vr::vr_fused_kernel<true, 42>},   // CMU mocap markers
+};
+const int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
+KernelFn pick_kernel(bool fma, int vm) {
+    KernelFn generic = nullptr;
+    for (int i = 0; i < kNumVariants; ++i) {
+        if (kVariants[i].fma != fma) continue;
+        if (kVariants[i].vm == vm) return kVariants[i].fn;
+        if (kVariants[i].vm == 0) generic = kVariants[i].fn;
+    }
+    return generic;
+}
+
 struct DeviceInfo { int sm_count = 0; bool attr_set = false; };
 std::mutex g_mu;
 DeviceInfo g_dev[64];
@@ -190,8 +219,8 @@ int device_setup(int& dev, int& sm_count) {
         if (prop.major < 10)
             return fail(VR_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", dev, prop.major, prop.minor);
         d.sm_count = prop.multiProcessorCount;
-        CUDA_TRY(cudaFuncSetAttribute(vr::vr_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-        CUDA_TRY(cudaFuncSetAttribute(vr::vr_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        for (int i = 0; i < kNumVariants; ++i)
+            CUDA_TRY(cudaFuncSetAttribute(kVariants[i].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         d.attr_set = true;
     }
     sm_count = d.sm_count;
@@ -215,10 +244,7 @@ int launch(const float* x, int64_t N, int64_t T, int V, int M, const int32_t* sr
     p.lam_ptr = lam_dev; p.loc_ptr = loc_dev;
     p.lam_val = lam_val;
     if (loc_val) { p.loc_val[0] = loc_val[0]; p.loc_val[1] = loc_val[1]; p.loc_val[2] = loc_val[2]; }
-    if (flags & VR_FLAG_RANGE_FMA)
-        vr::vr_fused_kernel<true><<<grid, p.W * 32, p.smem_bytes, stream>>>(p);
-    else
-        vr::vr_fused_kernel<false><<<grid, p.W * 32, p.smem_bytes, stream>>>(p);
+    pick_kernel((flags & VR_FLAG_RANGE_FMA) != 0, p.VM)<<<grid, p.W * 32, p.smem_bytes, stream>>>(p);
     CUDA_TRY(cudaGetLastError());
     return VR_OK;
 }
@@ -345,6 +371,22 @@ int vr_plan(int64_t N, int64_t T, int32_t V, int32_t M, const int32_t* src_host,
     plan[0] = grid; plan[1] = p.W * 32; plan[2] = p.smem_bytes; plan[3] = p.S; plan[4] = p.FJ;
     plan[5] = p.jobs_per_seq; plan[6] = p.FB; plan[7] = p.tma_in; plan[8] = p.bulk_out; plan[9] = p.cmax;
     plan[10] = p.eg_max; plan[11] = p.sg_max; plan[12] = p.zcap; plan[13] = cps; plan[14] = vr::TL; plan[15] = vr::NG;
+    return VR_OK;
+}
+
+int vr_selftest_rounding(uint64_t n, float wavelength, uint64_t mismatches[3]) {
+    if (!mismatches) return fail(VR_ERR_ARG, "mismatches must not be null");
+    unsigned long long* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, 3 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(d, 0, 3 * sizeof(unsigned long long)));
+    vr::vr_selftest_kernel<<<1184, 256>>>(n, wavelength, d);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    unsigned long long h[3] = {0, 0, 0};
+    if (e == cudaSuccess) e = cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(VR_ERR_CUDA, "selftest: %s", cudaGetErrorString(e));
+    for (int i = 0; i < 3; ++i) mismatches[i] = h[i];
     return VR_OK;
 }
 

@@ -184,6 +184,13 @@ def test_stream_and_no_sync():
     assert torch.equal(y, ref)
 
 
+def test_fast_rounding_sequences_equal_ieee_intrinsics():
+    """The branch-free sqrt/divide sequences in the kernel == __fsqrt_rn / __fdiv_rn, bit for bit."""
+    from skeleton_action_recognition_b200 import _cabi
+    for lam in (5e-4, 9e-4, 1e-3, 5e-3, 2e-3, 1.2345e-2):
+        assert _cabi.selftest_rounding(1 << 26, lam) == [0, 0, 0], lam
+
+
 def test_errors_on_gpu_inputs():
     layer = _layer(wavelength=5e-4)
     with pytest.raises(ValueError, match="exceed n_fft/2"):
