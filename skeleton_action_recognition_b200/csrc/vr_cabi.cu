@@ -137,6 +137,7 @@ int make_plan(int64_t N, int64_t T, int V, int M, const int32_t* src, const int3
     p.FJ = (p.F + p.jobs_per_seq - 1) / p.jobs_per_seq;
     p.jobs_per_seq = (p.F + p.FJ - 1) / p.FJ;
     p.n_jobs = N * (long long)p.jobs_per_seq;
+    if (p.n_jobs >= (1ll << 31) / 2) return fail(VR_ERR_UNSUPPORTED, "N*jobs_per_seq=%lld too large for one launch; split the batch", p.n_jobs);
     int zspan = 0, cmax = 0;
     for (int j = 0; j < p.jobs_per_seq; ++j) {
         vr::JobGeom g = vr::job_geom(j, p.jobs_per_seq, p.FJ, p.F, hop, (int)T);
@@ -155,7 +156,7 @@ int make_plan(int64_t N, int64_t T, int V, int M, const int32_t* src, const int3
     int W = g_tuning.warps > 0 ? g_tuning.warps : 8;
     W = std::min(W, vr::MAX_WARPS);
     p.W = W;
-    p.scr_bytes = round_up(std::max(vr::XCH_BYTES, p.eg_max * 128), 128);
+    p.scr_bytes = round_up(std::max(vr::XCH_BYTES, p.eg_max * 128 * ((M % 2 == 0) ? 2 : 1)), 128);
     int off = 0;
     off += round_up(2 * vr::MAX_WARPS * (8 + 4), 128);                  // mbarriers + issued sequence numbers (S <= 2*MAX_WARPS)
     p.off_tab = off; off += (vr::NG * vr::MAX_EG + vr::NG * vr::MAX_SG) * 4;
@@ -185,19 +186,21 @@ int make_plan(int64_t N, int64_t T, int V, int M, const int32_t* src, const int3
 
 // kernel variants: range rounding mode x compile-time V*M (plane stride as an immediate); VM=0 is generic
 typedef void (*KernelFn)(const vr::Params);
-struct Variant { bool fma; int vm; KernelFn fn; };
+struct Variant { bool fma; int vm; int nb; KernelFn fn; };
+#define VR_VARIANT(VM, NB) {false, VM, NB, vr::vr_fused_kernel<false, VM, NB>}, {true, VM, NB, vr::vr_fused_kernel<true, VM, NB>}
 const Variant kVariants[] = {
-    {false, 0, vr::vr_fused_kernel<false, 0>},   {true, 0, vr::vr_fused_kernel<true, 0>},
-    {false, 50, vr::vr_fused_kernel<false, 50>}, {true, 50, vr::vr_fused_kernel<true, 50>},   // NTU, two bodies
-    {false, 25, vr::vr_fused_kernel<false, 25>}, {true, 25, vr::vr_fused_kernel<true, 25>},   // NTU, one body
-    {false, 17, vr::vr_fused_kernel<false, 17>}, {true, 17, vr::vr_fused_kernel<true, 17>},   // simulated gait
-    {false, 42, vr::vr_fused_kernel<false, 42>}, {true, 42, vr::vr_fused_kernel<true, 42>},   // CMU mocap markers
+    VR_VARIANT(0, 1), VR_VARIANT(0, 2),     // generic V*M: one body at a time / two bodies at a time (M even)
+    VR_VARIANT(50, 2),                      // NTU, two bodies
+    VR_VARIANT(25, 1),                      // NTU, one body
+    VR_VARIANT(17, 1),                      // simulated gait
+    VR_VARIANT(42, 1),                      // CMU mocap markers
 };
 const int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
-KernelFn pick_kernel(bool fma, int vm) {
+KernelFn pick_kernel(bool fma, int vm, int m) {
+    const int nb = (m % 2 == 0) ? 2 : 1;
     KernelFn generic = nullptr;
     for (int i = 0; i < kNumVariants; ++i) {
-        if (kVariants[i].fma != fma) continue;
+        if (kVariants[i].fma != fma || kVariants[i].nb != nb) continue;
         if (kVariants[i].vm == vm) return kVariants[i].fn;
         if (kVariants[i].vm == 0) generic = kVariants[i].fn;
     }
@@ -244,7 +247,7 @@ int launch(const float* x, int64_t N, int64_t T, int V, int M, const int32_t* sr
     p.lam_ptr = lam_dev; p.loc_ptr = loc_dev;
     p.lam_val = lam_val;
     if (loc_val) { p.loc_val[0] = loc_val[0]; p.loc_val[1] = loc_val[1]; p.loc_val[2] = loc_val[2]; }
-    pick_kernel((flags & VR_FLAG_RANGE_FMA) != 0, p.VM)<<<grid, p.W * 32, p.smem_bytes, stream>>>(p);
+    pick_kernel((flags & VR_FLAG_RANGE_FMA) != 0, p.VM, p.M)<<<grid, p.W * 32, p.smem_bytes, stream>>>(p);
     CUDA_TRY(cudaGetLastError());
     return VR_OK;
 }
