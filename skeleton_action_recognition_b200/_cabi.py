@@ -5,7 +5,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libvirtual_radar_b200.so")
+LIB_PATH = os.environ.get("VR_B200_LIB_OVERRIDE") or os.path.join(_HERE, "lib", "libvirtual_radar_b200.so")  # override: build experiments only
 
 VR_OK, VR_ERR_ARG, VR_ERR_SHAPE, VR_ERR_UNSUPPORTED, VR_ERR_CUDA = 0, -1, -2, -3, -4
 VR_FLAG_RANGE_FMA = 1

@@ -100,6 +100,7 @@ int make_plan(int64_t N, int64_t T, int V, int M, const int32_t* src, const int3
     p.N = N; p.T = T; p.V = V; p.M = M; p.E = E; p.hop = hop; p.VM = V * M;
     p.F = (int)(T / hop) + 1;
     p.inv_E = 1.0f / (float)E;
+    p.negzero = -0.0f;
     p.plane_floats = vr::TL * p.VM;
     p.stage_bytes = round_up(3 * p.plane_floats * 4, 128);
     p.tma_in = (x_aligned && ((T * p.VM) % 4 == 0)) ? 1 : 0;
@@ -154,7 +155,7 @@ int make_plan(int64_t N, int64_t T, int V, int M, const int32_t* src, const int3
 
     // warps / CTAs per SM / ring depth
     int W = g_tuning.warps > 0 ? g_tuning.warps : 8;
-    W = std::min(W, vr::MAX_WARPS);
+    W = std::min(W, std::min(vr::MAX_WARPS, VR_LB_THREADS / 32));
     p.W = W;
     p.scr_bytes = round_up(std::max(vr::XCH_BYTES, p.eg_max * 128 * ((M % 2 == 0) ? 2 : 1)), 128);
     int off = 0;
