@@ -60,7 +60,7 @@ int partition_edges(const int32_t* src, const int32_t* dst, int E, int V, Partit
     }
     std::vector<int> order(joints.size());
     for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
-    const int COST_J = 36, COST_E = 39;
+    const int COST_J = 55, COST_E = 61;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return out[a].size() > out[b].size(); });
     long load[vr::NG] = {0, 0, 0, 0};
     for (int g = 0; g < vr::NG; ++g) { P.src_of[g].clear(); P.edges_of[g].clear(); P.ne[g] = P.ns[g] = 0; }
@@ -105,7 +105,7 @@ int make_plan(int64_t N, int64_t T, int V, int M, const int32_t* src, const int3
     p.stage_bytes = round_up(3 * p.plane_floats * 4, 128);
     p.tma_in = (x_aligned && ((T * p.VM) % 4 == 0)) ? 1 : 0;
 
-    // tables
+    // tables (warp-uniform in the kernel: one bone group per warp of a team)
     p.eg_max = p.sg_max = 0;
     for (int g = 0; g < vr::NG; ++g) {
         p.ne[g] = P.ne[g]; p.ns[g] = P.ns[g];
@@ -115,19 +115,11 @@ int make_plan(int64_t N, int64_t T, int V, int M, const int32_t* src, const int3
         for (size_t s = 0; s < P.src_of[g].size(); ++s) {
             const int eb = ei;
             for (int e : P.edges_of[g][s]) {
-                p.etab[ei * vr::NG + g] = (uint32_t)(src[e] * M * 4) | ((uint32_t)(dst[e] * M * 4) << 16);
+                p.etab[g * vr::MAX_EG + ei] = (uint32_t)(src[e] * M * 4) | ((uint32_t)(dst[e] * M * 4) << 16);
                 ++ei;
             }
-            p.stab[s * vr::NG + g] = (uint32_t)(P.src_of[g][s] * M * 4) | ((uint32_t)eb << 16) | ((uint32_t)ei << 24);
+            p.stab[g * vr::MAX_SG + s] = (uint32_t)(P.src_of[g][s] * M * 4) | ((uint32_t)eb << 16) | ((uint32_t)ei << 24);
         }
-    }
-    // padding entries: a zero-length bone (src == dst) on a joint that some real bone uses, so that
-    // it adds exactly 0 to the bone-length sum and can only be NaN if the reference's output is NaN;
-    // padding source joints carry an empty bone range and are masked in the kernel.
-    for (int g = 0; g < vr::NG; ++g) {
-        const uint32_t j = (uint32_t)((P.src_of[g].empty() ? src[0] : P.src_of[g][0]) * M * 4);
-        for (int ei = P.ne[g]; ei < p.eg_max; ++ei) p.etab[ei * vr::NG + g] = j | (j << 16);
-        for (int si = P.ns[g]; si < p.sg_max; ++si) p.stab[si * vr::NG + g] = j;
     }
 
     // jobs: frames per job bounded by the z buffer
@@ -153,28 +145,32 @@ int make_plan(int64_t N, int64_t T, int V, int M, const int32_t* src, const int3
     if (p.jobs_per_seq == 1 && p.F <= FB_BULK_MAX) { p.FB = p.F; p.ostride = p.F; p.bulk_out = 1; }
     else { p.FB = 16; p.ostride = 17; p.bulk_out = 0; }
 
-    // warps / CTAs per SM / ring depth
+    // consumer warps (teams of NG) / CTAs per SM / ring depth
     int W = g_tuning.warps > 0 ? g_tuning.warps : 8;
-    W = std::min(W, std::min(vr::MAX_WARPS, VR_LB_THREADS / 32));
+    W = std::min(W, std::min(vr::MAX_WARPS, VR_LB_THREADS / 32 - 1));
+    W = std::max(vr::NG, W / vr::NG * vr::NG);
     p.W = W;
-    p.scr_bytes = round_up(std::max(vr::XCH_BYTES, p.eg_max * 128 * ((M % 2 == 0) ? 2 : 1)), 128);
+    const int NB = (M % 2 == 0) ? 2 : 1;
+    p.scr_bytes = round_up(std::max(vr::XCH_BYTES, p.eg_max * 128 * NB), 128);
+    p.xg_bytes = round_up(vr::NG * 32 * NB * 4 + vr::NG * 32 * 8, 128);
     int off = 0;
-    off += round_up(2 * vr::MAX_WARPS * (8 + 4), 128);                  // mbarriers + issued sequence numbers (S <= 2*MAX_WARPS)
-    p.off_tab = off; off += (vr::NG * vr::MAX_EG + vr::NG * vr::MAX_SG) * 4;
+    off += round_up(2 * vr::MAX_STAGES * 8, 128);                        // full[] and empty[] mbarriers
     p.off_tw = off;  off += vr::NFFT * 8;
     p.off_z = off;   off += round_up(p.zcap * 8, 128);
     p.off_o = off;   off += round_up(vr::NFFT * p.ostride * 4, 128);
     p.off_scr = off; off += W * p.scr_bytes;
+    p.off_xg = off;  off += (W / vr::NG) * p.xg_bytes;
     p.off_ring = off;
     const int SMEM_SM = 233472, SMEM_CTA_MAX = 232448;
+    const int teams = W / vr::NG;
     ctas_per_sm = g_tuning.ctas_per_sm > 0 ? g_tuning.ctas_per_sm : 2;
     int S = 0;
     for (; ctas_per_sm >= 1; --ctas_per_sm) {
         int budget = std::min(SMEM_SM / ctas_per_sm - 1024, SMEM_CTA_MAX);
         S = (budget - off) / p.stage_bytes;
-        S = std::min(S, 2 * W);
+        S = std::min(S, std::min(vr::MAX_STAGES, 3 * teams));
         if (g_tuning.stages > 0) S = std::min(S, g_tuning.stages);
-        if (S >= std::min(4, 2 * W) || (ctas_per_sm == 1 && S >= 2)) break;
+        if (S >= teams + 1 || (ctas_per_sm == 1 && S >= 2)) break;
     }
     if (ctas_per_sm < 1 || S < 2)
         return fail(VR_ERR_UNSUPPORTED, "V*M=%d needs %d-byte chunks; no room for a load ring in shared memory", p.VM, p.stage_bytes);
@@ -248,7 +244,7 @@ int launch(const float* x, int64_t N, int64_t T, int V, int M, const int32_t* sr
     p.lam_ptr = lam_dev; p.loc_ptr = loc_dev;
     p.lam_val = lam_val;
     if (loc_val) { p.loc_val[0] = loc_val[0]; p.loc_val[1] = loc_val[1]; p.loc_val[2] = loc_val[2]; }
-    pick_kernel((flags & VR_FLAG_RANGE_FMA) != 0, p.VM, p.M)<<<grid, p.W * 32, p.smem_bytes, stream>>>(p);
+    pick_kernel((flags & VR_FLAG_RANGE_FMA) != 0, p.VM, p.M)<<<grid, (p.W + 1) * 32, p.smem_bytes, stream>>>(p);
     CUDA_TRY(cudaGetLastError());
     return VR_OK;
 }
@@ -372,7 +368,7 @@ int vr_plan(int64_t N, int64_t T, int32_t V, int32_t M, const int32_t* src_host,
     int grid, cps;
     int rc = make_plan(N, T, V, M, src_host, dst_host, E, n_fft, hop, sm_count > 0 ? sm_count : 148, true, p, grid, cps);
     if (rc) return rc;
-    plan[0] = grid; plan[1] = p.W * 32; plan[2] = p.smem_bytes; plan[3] = p.S; plan[4] = p.FJ;
+    plan[0] = grid; plan[1] = (p.W + 1) * 32; plan[2] = p.smem_bytes; plan[3] = p.S; plan[4] = p.FJ;
     plan[5] = p.jobs_per_seq; plan[6] = p.FB; plan[7] = p.tma_in; plan[8] = p.bulk_out; plan[9] = p.cmax;
     plan[10] = p.eg_max; plan[11] = p.sg_max; plan[12] = p.zcap; plan[13] = cps; plan[14] = vr::TL; plan[15] = vr::NG;
     return VR_OK;

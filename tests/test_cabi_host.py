@@ -38,9 +38,10 @@ def test_plan_ntu(cabi):
     p = cabi.plan(256, 300, 25, 2, src, dst)
     assert p["frames_per_job"] == 19 and p["jobs_per_seq"] == 1 and p["grid"] == 256
     assert p["tma_loads"] == 1 and p["tma_bulk_store"] == 1
-    assert p["chunks_per_job"] == 38 and p["chunk_steps"] == 8
+    assert p["chunks_per_job"] == 10 and p["chunk_steps"] == 32
+    assert p["block"] == 288 and p["ring_stages"] >= 3
     assert p["smem_bytes"] <= 232448 // 2
-    assert p["max_bones_per_group"] == 6
+    assert p["max_bones_per_group"] <= 7
     p = cabi.plan(65536, 300, 25, 2, src, dst)
     assert p["grid"] == 148 * p["ctas_per_sm"]
     p = cabi.plan(1, 165000, 25, 1, src, dst)
@@ -60,7 +61,7 @@ def test_partition_keeps_sources_together_and_balances(cabi):
         by_src.setdefault(s, set()).add(g)
     assert all(len(v) == 1 for v in by_src.values())
     counts = [grp.count(g) for g in range(4)]
-    assert max(counts) == 6 and min(counts) == 6
+    assert max(counts) <= 7 and min(counts) >= 5
     chain = [(i, i + 1) for i in range(41)]
     s2, d2 = map(list, zip(*chain))
     g2 = cabi.partition_edges(s2, d2, 42)
