@@ -105,21 +105,27 @@ int make_plan(int64_t N, int64_t T, int V, int M, const int32_t* src, const int3
     p.stage_bytes = round_up(3 * p.plane_floats * 4, 128);
     p.tma_in = (x_aligned && ((T * p.VM) % 4 == 0)) ? 1 : 0;
 
-    // tables (warp-uniform in the kernel: one bone group per warp of a team)
+    // tables (warp-uniform in the kernel: one bone group per warp of a team); within a group the
+    // source joints with exactly one bone are listed first (the kernel runs them two at a time)
     p.eg_max = p.sg_max = 0;
     for (int g = 0; g < vr::NG; ++g) {
-        p.ne[g] = P.ne[g]; p.ns[g] = P.ns[g];
+        p.ne[g] = P.ne[g]; p.ns[g] = P.ns[g]; p.ns1[g] = 0;
         p.eg_max = std::max(p.eg_max, P.ne[g]);
         p.sg_max = std::max(p.sg_max, P.ns[g]);
-        int ei = 0;
-        for (size_t s = 0; s < P.src_of[g].size(); ++s) {
-            const int eb = ei;
-            for (int e : P.edges_of[g][s]) {
-                p.etab[g * vr::MAX_EG + ei] = (uint32_t)(src[e] * M * 4) | ((uint32_t)(dst[e] * M * 4) << 16);
-                ++ei;
+        int ei = 0, si = 0;
+        for (int pass = 0; pass < 2; ++pass)
+            for (size_t s = 0; s < P.src_of[g].size(); ++s) {
+                const bool single = P.edges_of[g][s].size() == 1;
+                if (single != (pass == 0)) continue;
+                const int eb = ei;
+                for (int e : P.edges_of[g][s]) {
+                    p.etab[g * vr::MAX_EG + ei] = (uint32_t)(src[e] * M * 4) | ((uint32_t)(dst[e] * M * 4) << 16);
+                    ++ei;
+                }
+                p.stab[g * vr::MAX_SG + si] = (uint32_t)(P.src_of[g][s] * M * 4) | ((uint32_t)eb << 16) | ((uint32_t)ei << 24);
+                ++si;
+                if (single) p.ns1[g]++;
             }
-            p.stab[g * vr::MAX_SG + s] = (uint32_t)(P.src_of[g][s] * M * 4) | ((uint32_t)eb << 16) | ((uint32_t)ei << 24);
-        }
     }
 
     // jobs: frames per job bounded by the z buffer
