@@ -101,6 +101,12 @@ int vr_selftest_rounding(uint64_t n, float wavelength, uint64_t mismatches[3]);
  * targeted (<=4), cap on TMA ring stages.  Not needed for normal use.                             */
 int vr_set_tuning(int warps, int ctas_per_sm, int stages);
 
+/* Profiling aid (process-wide; NULL = off, the default): when set, every CTA of subsequent launches
+ * writes 8 uint64 to dev_buf[8*blockIdx.x ..]: %globaltimer (ns) at [0] entry, [1] prologue done,
+ * [2] first chunk landed, [3] first job's synthesis done, [4] first job's STFT done, [5] exit;
+ * [7] = %smid.  The buffer must hold 8 * grid entries (grid from vr_plan).                        */
+int vr_set_timeline_buffer(void* dev_u64_8_per_cta);
+
 #ifdef __cplusplus
 }
 #endif

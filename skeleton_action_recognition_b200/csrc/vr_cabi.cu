@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -31,6 +32,8 @@ int fail(int code, const char* fmt, ...) {
 
 struct Tuning { int warps = 0, ctas_per_sm = 0, stages = 0; };
 Tuning g_tuning;
+unsigned long long* g_timeline = nullptr;
+const bool g_pdl = getenv("VR_B200_NO_PDL") == nullptr;   // programmatic dependent launch (A/B switch for profiling)   // profiling only (vr_set_timeline_buffer)
 
 // ---- bone partition -----------------------------------------------------------------------------
 // Bones are grouped by source joint (the range phase of a joint is shared by all bones that start
@@ -158,11 +161,11 @@ int make_plan(int64_t N, int64_t T, int V, int M, const int32_t* src, const int3
     p.W = W;
     const int NB = (M % 2 == 0) ? 2 : 1;
     p.scr_bytes = round_up(std::max(vr::XCH_BYTES, p.eg_max * 128 * NB), 128);
-    p.xg_bytes = round_up(vr::NG * 32 * NB * 4 + vr::NG * 32 * 8, 128);
+    p.xg_bytes = round_up(2 * vr::NG * 32 * NB * 4, 128);        // double-buffered
     int off = 0;
     off += round_up(2 * vr::MAX_STAGES * 8, 128);                        // full[] and empty[] mbarriers
     p.off_tw = off;  off += vr::NFFT * 8;
-    p.off_z = off;   off += round_up(p.zcap * 8, 128);
+    p.off_z = off;   off += round_up(vr::NG * p.zcap * 8, 128);        // one partial-sum plane per bone group
     p.off_o = off;   off += round_up(vr::NFFT * p.ostride * 4, 128);
     p.off_scr = off; off += W * p.scr_bytes;
     p.off_xg = off;  off += (W / vr::NG) * p.xg_bytes;
@@ -233,6 +236,39 @@ int device_setup(int& dev, int& sm_count) {
     return VR_OK;
 }
 
+// Plans depend only on shapes and the bone list; the last one is kept per host thread so that a
+// training loop calling forward() with the same shapes pays for partitioning and planning once.
+struct PlanCache {
+    bool valid = false;
+    int64_t N = 0, T = 0;
+    int V = 0, M = 0, E = 0, n_fft = 0, hop = 0, sm_count = 0, grid = 0, cps = 0;
+    bool aligned = false;
+    Tuning tuning;
+    std::vector<int32_t> src, dst;
+    vr::Params p;
+};
+thread_local PlanCache t_plan;
+
+int cached_plan(int64_t N, int64_t T, int V, int M, const int32_t* src, const int32_t* dst, int E,
+                int n_fft, int hop, int sm_count, bool aligned, vr::Params& p, int& grid, int& cps) {
+    PlanCache& c = t_plan;
+    if (c.valid && c.N == N && c.T == T && c.V == V && c.M == M && c.E == E && c.n_fft == n_fft && c.hop == hop &&
+        c.sm_count == sm_count && c.aligned == aligned && src && dst &&
+        c.tuning.warps == g_tuning.warps && c.tuning.ctas_per_sm == g_tuning.ctas_per_sm && c.tuning.stages == g_tuning.stages &&
+        memcmp(c.src.data(), src, sizeof(int32_t) * E) == 0 && memcmp(c.dst.data(), dst, sizeof(int32_t) * E) == 0) {
+        p = c.p; grid = c.grid; cps = c.cps;
+        return VR_OK;
+    }
+    c.valid = false;
+    int rc = make_plan(N, T, V, M, src, dst, E, n_fft, hop, sm_count, aligned, p, grid, cps);
+    if (rc) return rc;
+    c.N = N; c.T = T; c.V = V; c.M = M; c.E = E; c.n_fft = n_fft; c.hop = hop; c.sm_count = sm_count; c.aligned = aligned;
+    c.tuning = g_tuning;
+    c.src.assign(src, src + E); c.dst.assign(dst, dst + E);
+    c.p = p; c.grid = grid; c.cps = cps; c.valid = true;
+    return VR_OK;
+}
+
 int launch(const float* x, int64_t N, int64_t T, int V, int M, const int32_t* src, const int32_t* dst, int E,
            const float* lam_dev, const float* loc_dev, float lam_val, const float* loc_val,
            int n_fft, int hop, uint32_t flags, float* out, float* iq, cudaStream_t stream) {
@@ -244,14 +280,23 @@ int launch(const float* x, int64_t N, int64_t T, int V, int M, const int32_t* sr
     if (rc) return rc;
     vr::Params p;
     int grid, cps;
-    rc = make_plan(N, T, V, M, src, dst, E, n_fft, hop, sm_count, ((uintptr_t)x & 15) == 0, p, grid, cps);
+    rc = cached_plan(N, T, V, M, src, dst, E, n_fft, hop, sm_count, ((uintptr_t)x & 15) == 0, p, grid, cps);
     if (rc) return rc;
-    p.x = x; p.out = out; p.iq = iq;
+    p.x = x; p.out = out; p.iq = iq; p.tl = g_timeline;
     p.lam_ptr = lam_dev; p.loc_ptr = loc_dev;
     p.lam_val = lam_val;
     if (loc_val) { p.loc_val[0] = loc_val[0]; p.loc_val[1] = loc_val[1]; p.loc_val[2] = loc_val[2]; }
-    pick_kernel((flags & VR_FLAG_RANGE_FMA) != 0, p.VM, p.M)<<<grid, (p.W + 1) * 32, p.smem_bytes, stream>>>(p);
-    CUDA_TRY(cudaGetLastError());
+    // Programmatic dependent launch: the kernel's prologue (barrier init, twiddle table) may overlap
+    // the tail of the previous kernel in the stream; the kernel executes griddepcontrol.wait before
+    // its first global-memory access, so stream order is preserved.
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)(p.W + 1) * 32);
+    cfg.dynamicSmemBytes = (size_t)p.smem_bytes; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, pick_kernel((flags & VR_FLAG_RANGE_FMA) != 0, p.VM, p.M), p));
     return VR_OK;
 }
 
@@ -364,6 +409,11 @@ int vr_release_host_staging(void) {
         sg.xcap = sg.ocap = 0;
     }
     cudaSetDevice(cur);
+    return VR_OK;
+}
+
+int vr_set_timeline_buffer(void* dev_u64_8_per_cta) {
+    g_timeline = static_cast<unsigned long long*>(dev_u64_8_per_cta);
     return VR_OK;
 }
 
