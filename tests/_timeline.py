@@ -20,7 +20,8 @@ names = ['entry', 'prologue', 'first_chunk', 'synth_done', 'fft_done', 'exit']
 print('event ms %.2f us, grid %d' % (e0.elapsed_time(e1) * 1e3, pl['grid']))
 for i, n in enumerate(names):
     v = (t[:, i] - t0) / 1e3
-    print('%-12s min %.2f  med %.2f  max %.2f us' % (n, v.min(), np.median(v), v.max()))
+    v = v[t[:, i] > 0]
+    if len(v): print("%-12s min %.2f  med %.2f  max %.2f us (%d CTAs)" % (n, v.min(), np.median(v), v.max(), len(v)))
 sm = t[:, 7]
 cnt = np.bincount(sm, minlength=148)
 for k in (1, 2):
