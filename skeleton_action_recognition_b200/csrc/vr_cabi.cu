@@ -163,7 +163,7 @@ int make_plan(int64_t N, int64_t T, int V, int M, const int32_t* src, const int3
     p.scr_bytes = round_up(std::max(vr::XCH_BYTES, p.eg_max * 128 * NB), 128);
     p.xg_bytes = round_up(2 * vr::NG * 32 * NB * 4, 128);        // double-buffered
     int off = 0;
-    off += round_up(2 * vr::MAX_STAGES * 8, 128);                        // full[] and empty[] mbarriers
+    off += round_up(vr::MAX_STAGES * (8 + 8 + 4), 128);                  // full[] / empty[] mbarriers, issued sequence numbers
     p.off_tw = off;  off += (7 * 32 + 7 * 4) * 16 + vr::NFFT * 4;        // pass-1 / pass-2 twiddles, Hann window
     p.off_z = off;   off += round_up(vr::NG * p.zcap * 8, 128);        // one partial-sum plane per bone group
     p.off_o = off;   off += round_up(vr::NFFT * p.ostride * 4, 128);
