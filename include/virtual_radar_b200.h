@@ -76,6 +76,15 @@ int vr_forward_host_f32(const float* x_host, int64_t N, int64_t T, int32_t V, in
                         float* out_host, int64_t sub_batch);
 int vr_release_host_staging(void);
 
+/* Temporal up-sampling of the joint trajectories to the radar sampling rate, the data loader's pre-stage:
+ * replaces `Dataset.pad_frames` (reference utils.py:134-140: scipy gaussian_filter1d(sigma) along time,
+ * then not-a-knot cubic interp1d to num_pad_frames*T frames, float64) together with the FloatTensor cast of
+ * `Dataset.__getitem__` (utils.py:128-132), for a whole batch on the device.
+ *   x_dev (N,3,T,V,M) float32 -> out_dev (N,3,num_pad_frames*T,V,M) float32, both contiguous; T >= 4.
+ * The reference default is num_pad_frames=250, sigma=3 (utils.py:105).                              */
+int vr_pad_frames_f32(const float* x_dev, int64_t N, int64_t T, int32_t V, int32_t M, int32_t num_pad_frames,
+                      float sigma, float* out_dev, void* stream);
+
 /* Host-side planning, callable without a GPU (used by tests and by bench.py's reporting).
  * vr_plan fills `plan[16]`:
  *   [0] grid  [1] block  [2] dynamic smem bytes  [3] ring stages  [4] frames per job

@@ -29,6 +29,13 @@ def dataset_pad_frames(sample, num_pad_frames=250, sigma=3):
     return spline(np.linspace(0, 1, num_pad_frames * frames))
 
 
+def dataset_getitem(sample, num_pad_frames=250, sigma=3):
+    """`Dataset.__getitem__` without the file access (utils.py:128-132): float32 sample (3,T,V,M) ->
+    pad_frames (float64) -> FloatTensor.  This is what the GPU `pad_frames` must reproduce."""
+    import torch
+    return torch.from_numpy(dataset_pad_frames(sample, num_pad_frames, sigma)).type(torch.FloatTensor)
+
+
 def notebook_tensor(data_tvc):
     """(T,V,C) float64 array -> the notebook's (1,3,T,V,1) float32 tensor with C-innermost
     strides (virtual_radar_example.ipynb cells 2-4: transpose(2,0,1), expand_dims, torch.Tensor)."""

@@ -14,7 +14,7 @@ ABI_VERSION = 1
 # every symbol include/virtual_radar_b200.h declares
 SYMBOLS = ("vr_abi_version", "vr_last_error", "vr_forward_f32", "vr_forward_debug_f32",
            "vr_forward_host_f32", "vr_release_host_staging", "vr_plan", "vr_partition_edges",
-           "vr_set_tuning", "vr_selftest_rounding", "vr_set_timeline_buffer")
+           "vr_set_tuning", "vr_selftest_rounding", "vr_set_timeline_buffer", "vr_pad_frames_f32")
 
 _lib = None
 
@@ -43,6 +43,8 @@ def lib():
     L.vr_plan.argtypes = [i64, i64, i32, i32, c_i32p, c_i32p, i32, i32, i32, i32, ctypes.POINTER(i64)]
     L.vr_partition_edges.argtypes = [c_i32p, c_i32p, i32, i32, c_i32p]
     L.vr_set_tuning.argtypes = [ctypes.c_int] * 3
+    L.vr_pad_frames_f32.argtypes = [vp, i64, i64, i32, i32, i32, f32, vp, vp]
+    L.vr_pad_frames_f32.restype = ctypes.c_int
     L.vr_set_timeline_buffer.argtypes = [vp]
     L.vr_set_timeline_buffer.restype = ctypes.c_int
     L.vr_selftest_rounding.argtypes = [ctypes.c_uint64, f32, ctypes.POINTER(ctypes.c_uint64)]

@@ -3,11 +3,13 @@
 // launch planning, and the pipelined host-buffer entry point.  No torch, no ATen.
 #include "../../include/virtual_radar_b200.h"
 #include "vr_kernels.cuh"
+#include "vr_pad_frames.cuh"
 
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -389,6 +391,57 @@ int vr_forward_host_f32(const float* x_host, int64_t N, int64_t T, int32_t V, in
     }
     CUDA_TRY(cudaStreamSynchronize(sg.st[0]));
     CUDA_TRY(cudaStreamSynchronize(sg.st[1]));
+    return VR_OK;
+}
+
+int vr_pad_frames_f32(const float* x_dev, int64_t N, int64_t T, int32_t V, int32_t M, int32_t num_pad_frames,
+                      float sigma, float* out_dev, void* stream) {
+    if (!x_dev || !out_dev) return fail(VR_ERR_ARG, "x_dev and out_dev must not be null");
+    if (N <= 0 || V <= 0 || M <= 0) return fail(VR_ERR_SHAPE, "N, V, M must be positive (got %lld, %d, %d)", (long long)N, V, M);
+    if (T < 4) return fail(VR_ERR_SHAPE, "T=%lld: cubic interpolation needs at least 4 frames (scipy interp1d raises ValueError)", (long long)T);
+    if (num_pad_frames < 1) return fail(VR_ERR_SHAPE, "num_pad_frames must be >= 1, got %d", num_pad_frames);
+    if (!(sigma > 0.f)) return fail(VR_ERR_SHAPE, "sigma must be positive, got %g", (double)sigma);
+    if ((double)T * num_pad_frames > 2.0e9) return fail(VR_ERR_UNSUPPORTED, "T*num_pad_frames too large");
+    int dev, sm_count;
+    int rc = device_setup(dev, sm_count);
+    if (rc) return rc;
+    vr::PadParams p;
+    memset(&p, 0, sizeof(p));
+    // scipy.ndimage._filters._gaussian_kernel1d(sigma, 0, radius), radius = int(4 * sigma + 0.5), float64
+    const double sd = (double)sigma;
+    p.radius = (int)(4.0 * sd + 0.5);
+    if (p.radius > vr::PF_MAX_RADIUS) return fail(VR_ERR_UNSUPPORTED, "sigma=%g needs a Gaussian radius of %d > %d", sd, p.radius, vr::PF_MAX_RADIUS);
+    {
+        double phi[2 * vr::PF_MAX_RADIUS + 1], sum = 0.0;
+        const double sigma2 = sd * sd;
+        for (int i = -p.radius; i <= p.radius; ++i) phi[i + p.radius] = exp(-0.5 / sigma2 * (double)(i * i));
+        for (int i = 0; i <= 2 * p.radius; ++i) sum += phi[i];
+        for (int j = 0; j <= p.radius; ++j) p.w[j] = phi[p.radius + j] / sum;
+    }
+    p.x = x_dev; p.out = out_dev;
+    p.planes = N * 3; p.T = (int)T; p.VM = V * M; p.K = num_pad_frames;
+    p.ratio = (double)(T - 1) / (double)((long long)num_pad_frames * T - 1);
+    // columns per CTA: 12 bytes per (frame, column) + 8 bytes per frame of shared memory
+    const long long budget = 200 * 1024 - 8ll * T;
+    long long nc = budget / (12ll * T);
+    if (nc < 1) return fail(VR_ERR_UNSUPPORTED, "T=%lld too long for the shared-memory spline solve (max %d frames)", (long long)T, 200 * 1024 / 20);
+    nc = std::min<long long>(nc, p.VM);
+    p.ncb = (int)((p.VM + nc - 1) / nc);
+    p.nc = (int)((p.VM + p.ncb - 1) / p.ncb);                    // even out the blocks
+    const size_t smem = (size_t)p.T * p.nc * 12 + (size_t)p.T * 8 + 16;
+    static std::mutex mu;
+    static bool attr_done[64] = {false};
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!attr_done[dev]) {
+            CUDA_TRY(cudaFuncSetAttribute(vr::vr_pad_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            attr_done[dev] = true;
+        }
+    }
+    const long long units = p.planes * p.ncb;
+    const int grid = (int)std::min<long long>(units, (long long)sm_count * 4);
+    vr::vr_pad_frames_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p);
+    CUDA_TRY(cudaGetLastError());
     return VR_OK;
 }
 

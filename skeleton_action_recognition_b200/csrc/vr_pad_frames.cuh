@@ -1,0 +1,120 @@
+// vr_pad_frames.cuh -- temporal up-sampling of joint trajectories to the radar sampling rate
+// (reference utils.py:134-140 `Dataset.pad_frames` followed by the FloatTensor cast of
+// `Dataset.__getitem__`, utils.py:128-132):
+//
+//   smooth = scipy.ndimage.gaussian_filter1d(x, sigma, axis=time)      float32 in -> float64 accumulate -> float32 out
+//   spline = scipy.interpolate.interp1d(linspace(0,1,T), smooth, 'cubic', axis=time)   not-a-knot cubic, float64
+//   out    = float32(spline(linspace(0,1,k*T)))
+//
+// One CTA owns the trajectories of `nc` adjacent (joint, body) columns of one (sequence, coordinate)
+// plane.  It (1) smooths them with the reflect-padded Gaussian in FP64, accumulating in scipy's order
+// (centre tap, then symmetric pairs from the outermost inwards) and rounding to float32 exactly where
+// scipy does; (2) solves the not-a-knot cubic spline for its second derivatives, one thread per
+// trajectory (the end conditions reduce the system to tridiagonal: 6 M1 = rhs1, 6 M(T-2) = rhs(T-2));
+// (3) evaluates the k*T output frames in FP64 from shared memory and writes float32 rows, coalesced.
+// The intermediate float64 arrays never leave shared memory.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vr {
+
+constexpr int PF_MAX_RADIUS = 40;
+
+struct PadParams {
+    const float* x;              // (N,3,T,V,M)
+    float* out;                  // (N,3,k*T,V,M)
+    long long planes;            // N*3
+    int T, VM, K, nc, ncb;       // frames in, columns per plane, up-sampling factor, columns per CTA, column blocks per plane
+    int radius;
+    double ratio;                // (T-1)/(K*T-1): input-sample position of output frame i is i*ratio
+    double w[PF_MAX_RADIUS + 1]; // Gaussian weights, w[0] = centre
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ int pf_reflect(int t, int T) {     // scipy 'reflect': d c b a | a b c d | d c b a
+    while (t < 0 || t >= T) t = t < 0 ? -t - 1 : 2 * T - t - 1;
+    return t;
+}
+
+__global__ void __launch_bounds__(256, 1) vr_pad_frames_kernel(const __grid_constant__ PadParams p) {
+    extern __shared__ __align__(16) unsigned char pf_smem[];
+    const int T = p.T, nc = p.nc;
+    double* Msh = reinterpret_cast<double*>(pf_smem);            // [T][nc] second derivatives (unit sample spacing)
+    double* cp = Msh + (size_t)T * nc;                           // [T]     Thomas coefficients (same for every column)
+    float* ys = reinterpret_cast<float*>(cp + T);                // [T][nc] smoothed trajectories, float32 like scipy's output
+    const int tid = threadIdx.x;
+    const long long KT = (long long)p.K * T;
+
+    for (long long unit = blockIdx.x; unit < p.planes * p.ncb; unit += gridDim.x) {
+        const long long plane = unit / p.ncb;
+        const int col0 = (int)(unit - plane * p.ncb) * nc;
+        const int ncl = (p.VM - col0 < nc) ? (p.VM - col0) : nc;     // columns of this block
+        const float* xp = p.x + plane * (long long)T * p.VM + col0;
+        float* op = p.out + plane * KT * p.VM + col0;
+        __syncthreads();                                         // previous unit's evaluation has finished with shared memory
+
+        // (1) Gaussian smoothing along time, float64 accumulate in scipy's order, float32 result
+        for (int idx = tid; idx < T * ncl; idx += blockDim.x) {
+            const int t = idx / ncl, c = idx - t * ncl;
+            double acc = __dmul_rn((double)__ldg(xp + (size_t)t * p.VM + c), p.w[0]);
+            for (int jj = p.radius; jj >= 1; --jj) {
+                const double a = (double)__ldg(xp + (size_t)pf_reflect(t - jj, T) * p.VM + c);
+                const double b = (double)__ldg(xp + (size_t)pf_reflect(t + jj, T) * p.VM + c);
+                acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(a, b), p.w[jj]));
+            }
+            ys[t * nc + c] = (float)acc;
+        }
+        if (tid == 0) {                                          // c'_i of the Thomas algorithm for rows 2..T-3 (diagonal 4, off-diagonals 1)
+            double c = 0.0;
+            for (int i = 2; i <= T - 3; ++i) { c = 1.0 / (4.0 - c); cp[i] = c; }
+        }
+        __syncthreads();
+
+        // (2) not-a-knot cubic spline: second derivatives M_i, one thread per trajectory
+        if (tid < ncl) {
+            const int c = tid;
+            auto rhs = [&](int i) {
+                return 6.0 * (((double)ys[(i - 1) * nc + c] - 2.0 * (double)ys[i * nc + c]) + (double)ys[(i + 1) * nc + c]);
+            };
+            const double M1 = rhs(1) / 6.0, Mn = rhs(T - 2) / 6.0;
+            Msh[1 * nc + c] = M1;
+            Msh[(T - 2) * nc + c] = Mn;
+            double d = 0.0;                                      // forward sweep: d'_i stored in place
+            for (int i = 2; i <= T - 3; ++i) {
+                double r = rhs(i);
+                if (i == 2) r -= M1;
+                if (i == T - 3) r -= Mn;
+                d = (r - d) * cp[i];
+                Msh[i * nc + c] = d;
+            }
+            double next = 0.0;                                   // back substitution: M_i = d'_i - c'_i M_{i+1}
+            for (int i = T - 3; i >= 2; --i) {
+                const double m = Msh[i * nc + c] - (i == T - 3 ? 0.0 : cp[i] * next);
+                Msh[i * nc + c] = m;
+                next = m;
+            }
+            Msh[0 * nc + c] = 2.0 * Msh[1 * nc + c] - Msh[2 * nc + c];
+            Msh[(T - 1) * nc + c] = 2.0 * Msh[(T - 2) * nc + c] - Msh[(T - 3) * nc + c];
+        }
+        __syncthreads();
+
+        // (3) evaluate the K*T output frames, float64, and write float32 rows
+        for (long long idx = tid; idx < KT * ncl; idx += blockDim.x) {
+            const long long i = idx / ncl;
+            const int c = (int)(idx - i * ncl);
+            const double s = (double)i * p.ratio;
+            int j = (int)s;
+            j = j > T - 2 ? T - 2 : j;
+            const double tt = s - (double)j;
+            const double y0 = (double)ys[j * nc + c], y1 = (double)ys[(j + 1) * nc + c];
+            const double m0 = Msh[j * nc + c], m1 = Msh[(j + 1) * nc + c];
+            const double b1 = (y1 - y0) - (2.0 * m0 + m1) * (1.0 / 6.0);
+            const double v = y0 + tt * (b1 + tt * (0.5 * m0 + tt * ((m1 - m0) * (1.0 / 6.0))));
+            op[i * p.VM + c] = (float)v;
+        }
+    }
+}
+#endif  // __CUDACC__
+
+}  // namespace vr
