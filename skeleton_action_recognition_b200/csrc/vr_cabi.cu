@@ -440,7 +440,7 @@ int vr_pad_frames_f32(const float* x_dev, int64_t N, int64_t T, int32_t V, int32
     }
     const long long units = p.planes * p.ncb;
     const int grid = (int)std::min<long long>(units, (long long)sm_count * 4);
-    vr::vr_pad_frames_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p);
+    vr::vr_pad_frames_kernel<<<grid, 1024, smem, (cudaStream_t)stream>>>(p);
     CUDA_TRY(cudaGetLastError());
     return VR_OK;
 }

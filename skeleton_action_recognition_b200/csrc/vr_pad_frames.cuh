@@ -37,7 +37,7 @@ __device__ __forceinline__ int pf_reflect(int t, int T) {     // scipy 'reflect'
     return t;
 }
 
-__global__ void __launch_bounds__(256, 1) vr_pad_frames_kernel(const __grid_constant__ PadParams p) {
+__global__ void __launch_bounds__(1024, 1) vr_pad_frames_kernel(const __grid_constant__ PadParams p) {
     extern __shared__ __align__(16) unsigned char pf_smem[];
     const int T = p.T, nc = p.nc;
     double* Msh = reinterpret_cast<double*>(pf_smem);            // [T][nc] second derivatives (unit sample spacing)
@@ -99,19 +99,31 @@ __global__ void __launch_bounds__(256, 1) vr_pad_frames_kernel(const __grid_cons
         }
         __syncthreads();
 
-        // (3) evaluate the K*T output frames, float64, and write float32 rows
-        for (long long idx = tid; idx < KT * ncl; idx += blockDim.x) {
-            const long long i = idx / ncl;
-            const int c = (int)(idx - i * ncl);
-            const double s = (double)i * p.ratio;
-            int j = (int)s;
-            j = j > T - 2 ? T - 2 : j;
-            const double tt = s - (double)j;
-            const double y0 = (double)ys[j * nc + c], y1 = (double)ys[(j + 1) * nc + c];
-            const double m0 = Msh[j * nc + c], m1 = Msh[(j + 1) * nc + c];
-            const double b1 = (y1 - y0) - (2.0 * m0 + m1) * (1.0 / 6.0);
-            const double v = y0 + tt * (b1 + tt * (0.5 * m0 + tt * ((m1 - m0) * (1.0 / 6.0))));
-            op[i * p.VM + c] = (float)v;
+        // (3) evaluate the K*T output frames, float64, and write float32 rows.  The plane's output is one
+        // contiguous run when the block holds all columns, so a flat index gives coalesced stores; (row, column)
+        // advance incrementally (no divisions) and the cubic of the current input interval is kept in
+        // registers while consecutive output frames fall into it (K frames per interval).
+        {
+            const int rows_per_step = (int)blockDim.x / ncl;     // threads beyond rows_per_step * ncl sit this phase out,
+            const int c = tid % ncl;                             // so that every thread stays on one column
+            int jc = -1;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            for (long long i = tid / ncl; i < KT && tid < rows_per_step * ncl; i += rows_per_step) {
+                const double s = (double)i * p.ratio;
+                int j = (int)s;
+                j = j > T - 2 ? T - 2 : j;
+                if (j != jc) {
+                    const double y0 = (double)ys[j * nc + c], y1 = (double)ys[(j + 1) * nc + c];
+                    const double m0 = Msh[j * nc + c], m1 = Msh[(j + 1) * nc + c];
+                    a0 = y0;
+                    a1 = (y1 - y0) - (2.0 * m0 + m1) * (1.0 / 6.0);
+                    a2 = 0.5 * m0;
+                    a3 = (m1 - m0) * (1.0 / 6.0);
+                    jc = j;
+                }
+                const double tt = s - (double)j;
+                op[i * p.VM + c] = (float)fma(tt, fma(tt, fma(tt, a3, a2), a1), a0);
+            }
         }
     }
 }
