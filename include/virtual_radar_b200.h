@@ -65,6 +65,20 @@ int vr_forward_debug_f32(const float* x_dev, int64_t N, int64_t T, int32_t V, in
                          int32_t n_fft, int32_t hop, uint32_t flags,
                          float* out_dev, float* iq_dev, void* stream);
 
+/* The layer fused with its consumer's input stage: reference models/resnet.py:24-26 applies
+ * `x.unsqueeze(1)` and `torch.nn.functional.interpolate(x, image_size)` (mode 'nearest') to the
+ * layer's output before the ResNet.  This entry writes that (N, 1, image_size, image_size) float32
+ * image directly: image row r shows spectrogram row min(floor(r * float(n_fft)/image_size), n_fft-1),
+ * image column c shows STFT frame min(floor(c * float(F)/image_size), F-1), F = T/hop + 1 (ATen's
+ * legacy nearest indexing).  Only the frames the resize keeps are transformed (for T = 75 000 that is
+ * 256 of 4 688), and the (N, n_fft, F) spectrogram never goes to HBM.  Values are bit-identical to
+ * vr_forward_f32 followed by the resize.                                                          */
+int vr_forward_image_f32(const float* x_dev, int64_t N, int64_t T, int32_t V, int32_t M,
+                         const int32_t* src_host, const int32_t* dst_host, int32_t E,
+                         const float* wavelength_dev, const float* radar_loc_dev,
+                         int32_t n_fft, int32_t hop, uint32_t flags, int32_t image_size,
+                         float* out_dev, void* stream);
+
 /* End-to-end entry with HOST buffers (x_host pinned for full speed): splits the batch into
  * sub-batches and pipelines H2D copy / fused kernel / D2H copy on two internal streams of the
  * current device.  Blocks until out_host is complete.  Staging buffers are owned by the library,
@@ -95,6 +109,12 @@ int vr_pad_frames_f32(const float* x_dev, int64_t N, int64_t T, int32_t V, int32
 int vr_plan(int64_t N, int64_t T, int32_t V, int32_t M,
             const int32_t* src_host, const int32_t* dst_host, int32_t E,
             int32_t n_fft, int32_t hop, int32_t sm_count, int64_t plan[16]);
+
+/* vr_plan for vr_forward_image_f32; same layout except [4] output columns per job, [10] 1 if the
+ * resize keeps fewer frames than the STFT has (only kept frames are transformed), [11] output columns. */
+int vr_plan_image(int64_t N, int64_t T, int32_t V, int32_t M,
+                  const int32_t* src_host, const int32_t* dst_host, int32_t E,
+                  int32_t n_fft, int32_t hop, int32_t image_size, int32_t sm_count, int64_t plan[16]);
 
 /* Bone -> lane-group assignment used by the synthesis stage (4 groups; all bones sharing a source
  * joint stay in one group so the range phase of that joint is evaluated once).  group_of_edge[E]. */

@@ -14,7 +14,8 @@ ABI_VERSION = 1
 # every symbol include/virtual_radar_b200.h declares
 SYMBOLS = ("vr_abi_version", "vr_last_error", "vr_forward_f32", "vr_forward_debug_f32",
            "vr_forward_host_f32", "vr_release_host_staging", "vr_plan", "vr_partition_edges",
-           "vr_set_tuning", "vr_selftest_rounding", "vr_set_timeline_buffer", "vr_pad_frames_f32")
+           "vr_set_tuning", "vr_selftest_rounding", "vr_set_timeline_buffer", "vr_pad_frames_f32",
+           "vr_forward_image_f32", "vr_plan_image")
 
 _lib = None
 
@@ -39,6 +40,8 @@ def lib():
     common = [vp, i64, i64, i32, i32, c_i32p, c_i32p, i32]
     L.vr_forward_f32.argtypes = common + [vp, vp, i32, i32, u32, vp, vp]
     L.vr_forward_debug_f32.argtypes = common + [vp, vp, i32, i32, u32, vp, vp, vp]
+    L.vr_forward_image_f32.argtypes = common + [vp, vp, i32, i32, u32, i32, vp, vp]
+    L.vr_plan_image.argtypes = [i64, i64, i32, i32, c_i32p, c_i32p, i32, i32, i32, i32, i32, ctypes.POINTER(i64)]
     L.vr_forward_host_f32.argtypes = common + [f32, ctypes.POINTER(f32), i32, i32, u32, vp, i64]
     L.vr_plan.argtypes = [i64, i64, i32, i32, c_i32p, c_i32p, i32, i32, i32, i32, ctypes.POINTER(i64)]
     L.vr_partition_edges.argtypes = [c_i32p, c_i32p, i32, i32, c_i32p]
@@ -49,7 +52,7 @@ def lib():
     L.vr_set_timeline_buffer.restype = ctypes.c_int
     L.vr_selftest_rounding.argtypes = [ctypes.c_uint64, f32, ctypes.POINTER(ctypes.c_uint64)]
     L.vr_selftest_rounding.restype = ctypes.c_int
-    for name in ("vr_forward_f32", "vr_forward_debug_f32", "vr_forward_host_f32", "vr_plan",
+    for name in ("vr_forward_f32", "vr_forward_debug_f32", "vr_forward_host_f32", "vr_plan", "vr_forward_image_f32", "vr_plan_image",
                  "vr_partition_edges", "vr_set_tuning", "vr_release_host_staging"):
         getattr(L, name).restype = ctypes.c_int
     if L.vr_abi_version() != ABI_VERSION:
@@ -88,6 +91,15 @@ def plan(N, T, V, M, src, dst, n_fft=256, hop=16, sm_count=148):
     out = (ctypes.c_int64 * 16)()
     check(lib().vr_plan(N, T, V, M, i32_array(src), i32_array(dst), len(src), n_fft, hop, sm_count, out))
     return dict(zip(PLAN_FIELDS, [int(v) for v in out]))
+
+
+IMAGE_PLAN_FIELDS = PLAN_FIELDS[:4] + ("columns_per_job",) + PLAN_FIELDS[5:10] + ("sparse_frames", "columns") + PLAN_FIELDS[12:]
+
+
+def plan_image(N, T, V, M, src, dst, image_size, n_fft=256, hop=16, sm_count=148):
+    out = (ctypes.c_int64 * 16)()
+    check(lib().vr_plan_image(N, T, V, M, i32_array(src), i32_array(dst), len(src), n_fft, hop, image_size, sm_count, out))
+    return dict(zip(IMAGE_PLAN_FIELDS, [int(v) for v in out]))
 
 
 def selftest_rounding(n, wavelength):

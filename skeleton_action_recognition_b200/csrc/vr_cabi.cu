@@ -89,7 +89,8 @@ int partition_edges(const int32_t* src, const int32_t* dst, int E, int V, Partit
 int round_up(int v, int a) { return (v + a - 1) / a * a; }
 
 int make_plan(int64_t N, int64_t T, int V, int M, const int32_t* src, const int32_t* dst, int E,
-              int n_fft, int hop, int sm_count, bool x_aligned, vr::Params& p, int& grid, int& ctas_per_sm) {
+              int n_fft, int hop, int img, int sm_count, bool x_aligned, vr::Params& p, int& grid, int& ctas_per_sm) {
+    if (img < 0 || img > 4096) return fail(VR_ERR_SHAPE, "image_size must be in [1, 4096], got %d", img);
     if (N <= 0 || T <= 0 || V <= 0 || M <= 0) return fail(VR_ERR_SHAPE, "N, T, V, M must be positive (got %lld, %lld, %d, %d)", (long long)N, (long long)T, V, M);
     if (hop <= 0) return fail(VR_ERR_SHAPE, "hop_length must be positive, got %d", hop);
     if (n_fft != vr::NFFT) return fail(VR_ERR_UNSUPPORTED, "this ABI version implements n_fft=256 only (got %d)", n_fft);
@@ -133,27 +134,57 @@ int make_plan(int64_t N, int64_t T, int V, int M, const int32_t* src, const int3
             }
     }
 
-    // jobs: frames per job bounded by the z buffer
+    // output columns: the frames themselves, or the image columns of the fused nearest resize
+    p.img = img;
+    p.ncols = img ? img : p.F;
+    p.cscale = img ? (float)p.F / (float)img : 1.f;          // ATen compute_scales_value<float>: float(in) / out
+    p.rscale = img ? (float)n_fft / (float)img : 1.f;
+    p.sparse = (img && p.F > img) ? 1 : 0;
+
+    // jobs: columns per job bounded by the z buffer
     const int ZCAP_MAX = 2304;
-    int fj_max = (ZCAP_MAX - vr::NFFT - 2 * vr::TL - 2) / hop + 1;
+    auto span_of = [&](int CJ, int& zspan, int& cmax, int& slots) {
+        const int jps = (p.ncols + CJ - 1) / CJ;
+        zspan = cmax = slots = 0;
+        for (int j = 0; j < jps; ++j) {
+            vr::JobGeom g = vr::job_geom(j, jps, CJ, p.ncols, p.img, p.cscale, p.F, hop, (int)T);
+            zspan = std::max(zspan, g.hi - g.lo + 1);
+            cmax = std::max(cmax, g.nchunks);
+            slots = std::max(slots, p.sparse ? g.nc : g.nf);
+        }
+    };
+    int fj_max = (ZCAP_MAX - vr::NFFT - 2 * vr::TL - 2) / hop + 1;     // frames whose span fits the z buffer
     if (fj_max < 1) return fail(VR_ERR_UNSUPPORTED, "hop_length=%d too large", hop);
-    p.jobs_per_seq = (p.F + fj_max - 1) / fj_max;
-    p.FJ = (p.F + p.jobs_per_seq - 1) / p.jobs_per_seq;
-    p.jobs_per_seq = (p.F + p.FJ - 1) / p.FJ;
+    int zspan = 0, cmax = 0, slots = 0;
+    if (!img) {
+        p.jobs_per_seq = (p.F + fj_max - 1) / fj_max;
+        p.FJ = (p.F + p.jobs_per_seq - 1) / p.jobs_per_seq;
+    } else {
+        // columns per job: start from the estimate frames/scale, shrink until the exact span fits
+        double est = (double)fj_max / std::max((double)p.cscale, 1e-6);
+        int CJ = (int)std::min<double>(std::max(est, 1.0), (double)p.ncols);
+        for (;;) {
+            int jps = (p.ncols + CJ - 1) / CJ;
+            CJ = (p.ncols + jps - 1) / jps;                               // even out the jobs (never grows CJ)
+            if (CJ >= 8 && jps > 1) CJ = CJ / 4 * 4;                      // keep job boundaries float4-aligned
+            span_of(CJ, zspan, cmax, slots);
+            if (zspan <= ZCAP_MAX || CJ == 1) break;
+            CJ = std::max(1, std::min(CJ - 1, CJ * ZCAP_MAX / zspan));
+        }
+        if (zspan > ZCAP_MAX) return fail(VR_ERR_UNSUPPORTED, "no job split fits the z buffer (T=%lld, hop=%d, image_size=%d)", (long long)T, hop, img);
+        p.FJ = CJ;
+    }
+    p.jobs_per_seq = (p.ncols + p.FJ - 1) / p.FJ;
     p.n_jobs = N * (long long)p.jobs_per_seq;
     if (p.n_jobs >= (1ll << 31) / 2) return fail(VR_ERR_UNSUPPORTED, "N*jobs_per_seq=%lld too large for one launch; split the batch", p.n_jobs);
-    int zspan = 0, cmax = 0;
-    for (int j = 0; j < p.jobs_per_seq; ++j) {
-        vr::JobGeom g = vr::job_geom(j, p.jobs_per_seq, p.FJ, p.F, hop, (int)T);
-        zspan = std::max(zspan, g.hi - g.lo + 1);
-        cmax = std::max(cmax, g.nchunks);
-    }
+    span_of(p.FJ, zspan, cmax, slots);
     p.zcap = round_up(zspan, 16);
     p.cmax = cmax;
 
     // output tile
     const int FB_BULK_MAX = 20;
-    if (p.jobs_per_seq == 1 && p.F <= FB_BULK_MAX) { p.FB = p.F; p.ostride = p.F; p.bulk_out = 1; }
+    if (!img && p.jobs_per_seq == 1 && p.F <= FB_BULK_MAX) { p.FB = p.F; p.ostride = p.F; p.bulk_out = 1; }
+    else if (img && slots <= FB_BULK_MAX) { p.FB = slots; p.ostride = slots | 1; p.bulk_out = 0; }
     else { p.FB = 16; p.ostride = 17; p.bulk_out = 0; }
 
     // consumer warps (teams of NG) / CTAs per SM / ring depth
@@ -187,8 +218,7 @@ int make_plan(int64_t N, int64_t T, int V, int M, const int32_t* src, const int3
         return fail(VR_ERR_UNSUPPORTED, "V*M=%d needs %d-byte chunks; no room for a load ring in shared memory", p.VM, p.stage_bytes);
     p.S = S;
     p.smem_bytes = off + S * p.stage_bytes;
-    long long slots = (long long)sm_count * ctas_per_sm;
-    grid = (int)std::min<long long>(p.n_jobs, slots);
+    grid = (int)std::min<long long>(p.n_jobs, (long long)sm_count * ctas_per_sm);
     return VR_OK;
 }
 
@@ -243,7 +273,7 @@ int device_setup(int& dev, int& sm_count) {
 struct PlanCache {
     bool valid = false;
     int64_t N = 0, T = 0;
-    int V = 0, M = 0, E = 0, n_fft = 0, hop = 0, sm_count = 0, grid = 0, cps = 0;
+    int V = 0, M = 0, E = 0, n_fft = 0, hop = 0, img = 0, sm_count = 0, grid = 0, cps = 0;
     bool aligned = false;
     Tuning tuning;
     std::vector<int32_t> src, dst;
@@ -252,9 +282,9 @@ struct PlanCache {
 thread_local PlanCache t_plan;
 
 int cached_plan(int64_t N, int64_t T, int V, int M, const int32_t* src, const int32_t* dst, int E,
-                int n_fft, int hop, int sm_count, bool aligned, vr::Params& p, int& grid, int& cps) {
+                int n_fft, int hop, int img, int sm_count, bool aligned, vr::Params& p, int& grid, int& cps) {
     PlanCache& c = t_plan;
-    if (c.valid && c.N == N && c.T == T && c.V == V && c.M == M && c.E == E && c.n_fft == n_fft && c.hop == hop &&
+    if (c.valid && c.N == N && c.T == T && c.V == V && c.M == M && c.E == E && c.n_fft == n_fft && c.hop == hop && c.img == img &&
         c.sm_count == sm_count && c.aligned == aligned && src && dst &&
         c.tuning.warps == g_tuning.warps && c.tuning.ctas_per_sm == g_tuning.ctas_per_sm && c.tuning.stages == g_tuning.stages &&
         memcmp(c.src.data(), src, sizeof(int32_t) * E) == 0 && memcmp(c.dst.data(), dst, sizeof(int32_t) * E) == 0) {
@@ -262,9 +292,9 @@ int cached_plan(int64_t N, int64_t T, int V, int M, const int32_t* src, const in
         return VR_OK;
     }
     c.valid = false;
-    int rc = make_plan(N, T, V, M, src, dst, E, n_fft, hop, sm_count, aligned, p, grid, cps);
+    int rc = make_plan(N, T, V, M, src, dst, E, n_fft, hop, img, sm_count, aligned, p, grid, cps);
     if (rc) return rc;
-    c.N = N; c.T = T; c.V = V; c.M = M; c.E = E; c.n_fft = n_fft; c.hop = hop; c.sm_count = sm_count; c.aligned = aligned;
+    c.N = N; c.T = T; c.V = V; c.M = M; c.E = E; c.n_fft = n_fft; c.hop = hop; c.img = img; c.sm_count = sm_count; c.aligned = aligned;
     c.tuning = g_tuning;
     c.src.assign(src, src + E); c.dst.assign(dst, dst + E);
     c.p = p; c.grid = grid; c.cps = cps; c.valid = true;
@@ -273,7 +303,7 @@ int cached_plan(int64_t N, int64_t T, int V, int M, const int32_t* src, const in
 
 int launch(const float* x, int64_t N, int64_t T, int V, int M, const int32_t* src, const int32_t* dst, int E,
            const float* lam_dev, const float* loc_dev, float lam_val, const float* loc_val,
-           int n_fft, int hop, uint32_t flags, float* out, float* iq, cudaStream_t stream) {
+           int n_fft, int hop, uint32_t flags, int img, float* out, float* iq, cudaStream_t stream) {
     if (!x || !out) return fail(VR_ERR_ARG, "x and out must not be null");
     if ((lam_dev == nullptr) != (loc_dev == nullptr)) return fail(VR_ERR_ARG, "wavelength and radar_location must both be device pointers or both be null");
     if (flags & ~VR_FLAG_RANGE_FMA) return fail(VR_ERR_ARG, "unknown flags 0x%x", flags);
@@ -282,7 +312,7 @@ int launch(const float* x, int64_t N, int64_t T, int V, int M, const int32_t* sr
     if (rc) return rc;
     vr::Params p;
     int grid, cps;
-    rc = cached_plan(N, T, V, M, src, dst, E, n_fft, hop, sm_count, ((uintptr_t)x & 15) == 0, p, grid, cps);
+    rc = cached_plan(N, T, V, M, src, dst, E, n_fft, hop, img, sm_count, ((uintptr_t)x & 15) == 0, p, grid, cps);
     if (rc) return rc;
     p.x = x; p.out = out; p.iq = iq; p.tl = g_timeline;
     p.lam_ptr = lam_dev; p.loc_ptr = loc_dev;
@@ -332,7 +362,7 @@ int vr_forward_f32(const float* x_dev, int64_t N, int64_t T, int32_t V, int32_t 
                    int32_t n_fft, int32_t hop, uint32_t flags, float* out_dev, void* stream) {
     if (!wavelength_dev || !radar_loc_dev) return fail(VR_ERR_ARG, "wavelength_dev and radar_loc_dev must not be null");
     return launch(x_dev, N, T, V, M, src_host, dst_host, E, wavelength_dev, radar_loc_dev, 0.f, nullptr,
-                  n_fft, hop, flags, out_dev, nullptr, (cudaStream_t)stream);
+                  n_fft, hop, flags, 0, out_dev, nullptr, (cudaStream_t)stream);
 }
 
 int vr_forward_debug_f32(const float* x_dev, int64_t N, int64_t T, int32_t V, int32_t M,
@@ -342,7 +372,31 @@ int vr_forward_debug_f32(const float* x_dev, int64_t N, int64_t T, int32_t V, in
     if (!wavelength_dev || !radar_loc_dev) return fail(VR_ERR_ARG, "wavelength_dev and radar_loc_dev must not be null");
     if (!iq_dev) return fail(VR_ERR_ARG, "iq_dev must not be null");
     return launch(x_dev, N, T, V, M, src_host, dst_host, E, wavelength_dev, radar_loc_dev, 0.f, nullptr,
-                  n_fft, hop, flags, out_dev, iq_dev, (cudaStream_t)stream);
+                  n_fft, hop, flags, 0, out_dev, iq_dev, (cudaStream_t)stream);
+}
+
+int vr_forward_image_f32(const float* x_dev, int64_t N, int64_t T, int32_t V, int32_t M,
+                         const int32_t* src_host, const int32_t* dst_host, int32_t E,
+                         const float* wavelength_dev, const float* radar_loc_dev,
+                         int32_t n_fft, int32_t hop, uint32_t flags, int32_t image_size,
+                         float* out_dev, void* stream) {
+    if (!wavelength_dev || !radar_loc_dev) return fail(VR_ERR_ARG, "wavelength_dev and radar_loc_dev must not be null");
+    if (image_size < 1) return fail(VR_ERR_SHAPE, "image_size must be positive, got %d", image_size);
+    return launch(x_dev, N, T, V, M, src_host, dst_host, E, wavelength_dev, radar_loc_dev, 0.f, nullptr,
+                  n_fft, hop, flags, image_size, out_dev, nullptr, (cudaStream_t)stream);
+}
+
+int vr_plan_image(int64_t N, int64_t T, int32_t V, int32_t M, const int32_t* src_host, const int32_t* dst_host,
+                  int32_t E, int32_t n_fft, int32_t hop, int32_t image_size, int32_t sm_count, int64_t plan[16]) {
+    if (!plan) return fail(VR_ERR_ARG, "plan must not be null");
+    vr::Params p;
+    int grid, cps;
+    int rc = make_plan(N, T, V, M, src_host, dst_host, E, n_fft, hop, image_size, sm_count > 0 ? sm_count : 148, true, p, grid, cps);
+    if (rc) return rc;
+    plan[0] = grid; plan[1] = (p.W + 1) * 32; plan[2] = p.smem_bytes; plan[3] = p.S; plan[4] = p.FJ;
+    plan[5] = p.jobs_per_seq; plan[6] = p.FB; plan[7] = p.tma_in; plan[8] = p.bulk_out; plan[9] = p.cmax;
+    plan[10] = p.sparse; plan[11] = p.ncols; plan[12] = p.zcap; plan[13] = cps; plan[14] = vr::TL; plan[15] = vr::NG;
+    return VR_OK;
 }
 
 int vr_forward_host_f32(const float* x_host, int64_t N, int64_t T, int32_t V, int32_t M,
@@ -385,7 +439,7 @@ int vr_forward_host_f32(const float* x_host, int64_t N, int64_t T, int32_t V, in
         const int64_t nb = std::min<int64_t>(sub_batch, N - n0);
         CUDA_TRY(cudaMemcpyAsync(sg.x[b], x_host + n0 * xseq, nb * xseq * 4, cudaMemcpyHostToDevice, sg.st[b]));
         rc = launch(sg.x[b], nb, T, V, M, src_host, dst_host, E, nullptr, nullptr, wavelength, radar_loc_host,
-                    n_fft, hop, flags, sg.o[b], nullptr, sg.st[b]);
+                    n_fft, hop, flags, 0, sg.o[b], nullptr, sg.st[b]);
         if (rc) { cudaStreamSynchronize(sg.st[0]); cudaStreamSynchronize(sg.st[1]); return rc; }
         CUDA_TRY(cudaMemcpyAsync(out_host + n0 * oseq, sg.o[b], nb * oseq * 4, cudaMemcpyDeviceToHost, sg.st[b]));
     }
@@ -475,7 +529,7 @@ int vr_plan(int64_t N, int64_t T, int32_t V, int32_t M, const int32_t* src_host,
     if (!plan) return fail(VR_ERR_ARG, "plan must not be null");
     vr::Params p;
     int grid, cps;
-    int rc = make_plan(N, T, V, M, src_host, dst_host, E, n_fft, hop, sm_count > 0 ? sm_count : 148, true, p, grid, cps);
+    int rc = make_plan(N, T, V, M, src_host, dst_host, E, n_fft, hop, 0, sm_count > 0 ? sm_count : 148, true, p, grid, cps);
     if (rc) return rc;
     plan[0] = grid; plan[1] = (p.W + 1) * 32; plan[2] = p.smem_bytes; plan[3] = p.S; plan[4] = p.FJ;
     plan[5] = p.jobs_per_seq; plan[6] = p.FB; plan[7] = p.tma_in; plan[8] = p.bulk_out; plan[9] = p.cmax;

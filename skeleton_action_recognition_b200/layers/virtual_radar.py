@@ -138,6 +138,33 @@ class VirtualRadar(torch.nn.Module):
         _cabi.check(rc)
         return out
 
+    def forward_image(self, x, image_size=256):
+        """The layer fused with its consumer's input stage (reference models/resnet.py:24-26):
+        equals `F.interpolate(self(x).unsqueeze(1), image_size)` (nearest) bit for bit, in one launch
+        that writes (N, 1, image_size, image_size) directly and transforms only the frames the
+        resize keeps."""
+        self._check_input(x)
+        if not x.is_cuda:
+            raise RuntimeError("VirtualRadar (B200) has no CPU path: move x to a CUDA device")
+        lam, loc = self.wavelength, self.radar_location
+        if lam.device != x.device or loc.device != x.device:
+            raise RuntimeError("module parameters are on %s but x is on %s; call .to(x.device)" % (lam.device, x.device))
+        image_size = int(image_size)
+        if image_size < 1:
+            raise ValueError("image_size must be positive, got %d" % image_size)
+        xc, flags = self._prepare(x)
+        N, _, T, V, M = xc.shape
+        out = torch.empty((N, 1, image_size, image_size), dtype=torch.float32, device=x.device)
+        if N == 0:
+            return out
+        with torch.cuda.device(x.device):
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            rc = _cabi.lib().vr_forward_image_f32(xc.data_ptr(), N, T, V, M, self._src_c, self._dst_c, len(self.src),
+                                                  lam.data_ptr(), loc.data_ptr(), self.n_fft, self.hop_length,
+                                                  flags, image_size, out.data_ptr(), ctypes.c_void_p(stream))
+        _cabi.check(rc)
+        return out
+
     def forward_debug(self, x):
         """forward plus the intermediate complex baseband signal (N,T,2); for stage-level parity tests."""
         self._check_input(x)

@@ -51,6 +51,28 @@ def test_plan_ntu(cabi):
     assert p["tma_loads"] == 0
 
 
+def test_plan_image(cabi):
+    """Launch plan of the fused resize (vr_forward_image_f32), host-only."""
+    from skeleton_action_recognition_b200 import edges
+    from oracle import resize
+    src, dst = map(list, zip(*edges))
+    p = cabi.plan_image(256, 300, 25, 2, src, dst, 256)
+    assert p["columns"] == 256 and p["columns_per_job"] == 256 and p["jobs_per_seq"] == 1 and p["sparse_frames"] == 0
+    assert p["frames_per_tile"] == 19 and p["tma_bulk_store"] == 0 and p["grid"] == 256
+    p = cabi.plan_image(4, 75000, 25, 2, src, dst, 256)          # 4688 frames, 256 kept
+    assert p["sparse_frames"] == 1 and p["columns"] == 256
+    assert p["jobs_per_seq"] * p["columns_per_job"] >= 256
+    # the widest job's samples fit the z buffer: (kept frames span) * hop + n_fft
+    kept = resize.nearest_index(256, 4688)
+    cj = p["columns_per_job"]
+    span = max((kept[min(c0 + cj, 256) - 1] - kept[c0]) * 16 + 256 for c0 in range(0, 256, cj))
+    assert span <= p["z_capacity"] <= 2304 + 16
+    p = cabi.plan_image(2, 3000, 25, 2, src, dst, 256)           # 188 frames -> dense, several jobs
+    assert p["sparse_frames"] == 0 and p["jobs_per_seq"] >= 2
+    with pytest.raises(ValueError):
+        cabi.plan_image(1, 300, 25, 2, src, dst, 5000)
+
+
 def test_partition_keeps_sources_together_and_balances(cabi):
     from skeleton_action_recognition_b200 import edges
     src, dst = map(list, zip(*edges))

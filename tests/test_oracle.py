@@ -146,3 +146,24 @@ def test_parity_metric_self():
     bad = y.copy()
     bad[:, 100:110] += 0.01
     assert not vro.parity_ok(vro.parity_report(bad, y))
+
+
+# ---- the consumer's nearest resize (models/resnet.py:24-26) -------------------------------------
+@pytest.mark.parametrize("in_size,out_size", [(19, 256), (256, 256), (19, 64), (19, 224), (19, 300), (19, 37),
+                                              (401, 256), (4688, 256), (188, 256), (512, 256), (128, 256),
+                                              (10313, 256), (300, 299), (7, 1), (1251, 1000)])
+def test_resize_restatement_matches_torch_interpolate(in_size, out_size):
+    from oracle import resize
+    x = torch.arange(in_size, dtype=torch.float32).reshape(1, 1, 1, in_size)
+    ref = torch.nn.functional.interpolate(x, (1, out_size)).reshape(-1).numpy().astype(np.int64)
+    assert np.array_equal(resize.nearest_index(out_size, in_size), ref)
+
+
+def test_resize_restatement_full_image():
+    from oracle import resize
+    g = torch.Generator().manual_seed(3)
+    spec = torch.randn(3, 256, 19, generator=g)
+    for size in (256, 224, 100, 513):
+        ref = torch.nn.functional.interpolate(spec.unsqueeze(1), size).numpy()
+        assert np.array_equal(resize.resize_nearest(spec.numpy(), size), ref)
+    assert len(resize.kept_frames(4688, 256)) == 256 and len(resize.kept_frames(19, 256)) == 19
