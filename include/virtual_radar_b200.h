@@ -99,6 +99,23 @@ int vr_release_host_staging(void);
 int vr_pad_frames_f32(const float* x_dev, int64_t N, int64_t T, int32_t V, int32_t M, int32_t num_pad_frames,
                       float sigma, float* out_dev, void* stream);
 
+/* The data loader's up-sampling fused in front of the layer: equals vr_pad_frames_f32 followed by
+ * vr_forward_f32 (image_size == 0; out_dev is (N, n_fft, num_pad_frames*T/hop + 1)) or by
+ * vr_forward_image_f32 (image_size > 0; out_dev is (N, 1, image_size, image_size)) bit for bit, but the
+ * (N,3,num_pad_frames*T,V,M) batch -- 45 MB per NTU sequence at the reference's 250 -- never exists:
+ * a small launch smooths the raw trajectories and solves the spline (the per-interval cubics go to
+ * `workspace_dev`, vr_upsampled_workspace_bytes(N,T,V,M) bytes, 1.4 MB per NTU sequence), and the radar
+ * kernel evaluates every 32-step chunk from them in shared memory, in float64, rounding to float32
+ * exactly where `Dataset.__getitem__` does (reference utils.py:128-140).  x_dev is the RAW (N,3,T,V,M)
+ * batch.  The up-sampled tensor the reference builds is standard-contiguous, so pass flags = 0.     */
+int64_t vr_upsampled_workspace_bytes(int64_t N, int64_t T, int32_t V, int32_t M);
+int vr_forward_upsampled_f32(const float* x_dev, int64_t N, int64_t T, int32_t V, int32_t M,
+                             const int32_t* src_host, const int32_t* dst_host, int32_t E,
+                             const float* wavelength_dev, const float* radar_loc_dev,
+                             int32_t n_fft, int32_t hop, uint32_t flags,
+                             int32_t num_pad_frames, float sigma, int32_t image_size,
+                             void* workspace_dev, int64_t workspace_bytes, float* out_dev, void* stream);
+
 /* Host-side planning, callable without a GPU (used by tests and by bench.py's reporting).
  * vr_plan fills `plan[16]`:
  *   [0] grid  [1] block  [2] dynamic smem bytes  [3] ring stages  [4] frames per job

@@ -88,8 +88,9 @@ int partition_edges(const int32_t* src, const int32_t* dst, int E, int V, Partit
 // ---- launch plan --------------------------------------------------------------------------------
 int round_up(int v, int a) { return (v + a - 1) / a * a; }
 
-int make_plan(int64_t N, int64_t T, int V, int M, const int32_t* src, const int32_t* dst, int E,
-              int n_fft, int hop, int img, int sm_count, bool x_aligned, vr::Params& p, int& grid, int& ctas_per_sm) {
+int make_plan_z(int64_t N, int64_t T, int V, int M, const int32_t* src, const int32_t* dst, int E,
+                int n_fft, int hop, int img, bool ups, int sm_count, bool x_aligned, int ZCAP_MAX, bool park,
+                vr::Params& p, int& grid, int& ctas_per_sm) {
     if (img < 0 || img > 4096) return fail(VR_ERR_SHAPE, "image_size must be in [1, 4096], got %d", img);
     if (N <= 0 || T <= 0 || V <= 0 || M <= 0) return fail(VR_ERR_SHAPE, "N, T, V, M must be positive (got %lld, %lld, %d, %d)", (long long)N, (long long)T, V, M);
     if (hop <= 0) return fail(VR_ERR_SHAPE, "hop_length must be positive, got %d", hop);
@@ -142,7 +143,6 @@ int make_plan(int64_t N, int64_t T, int V, int M, const int32_t* src, const int3
     p.sparse = (img && p.F > img) ? 1 : 0;
 
     // jobs: columns per job bounded by the z buffer
-    const int ZCAP_MAX = 2304;
     auto span_of = [&](int CJ, int& zspan, int& cmax, int& slots) {
         const int jps = (p.ncols + CJ - 1) / CJ;
         zspan = cmax = slots = 0;
@@ -198,10 +198,13 @@ int make_plan(int64_t N, int64_t T, int V, int M, const int32_t* src, const int3
     int off = 0;
     off += round_up(vr::MAX_STAGES * (8 + 8 + 4), 128);                  // full[] / empty[] mbarriers, issued sequence numbers
     p.off_tw = off;  off += (7 * 32 + 7 * 4) * 16 + vr::NFFT * 4;        // pass-1 / pass-2 twiddles, Hann window
-    p.off_z = off;   off += round_up(vr::NG * p.zcap * 8, 128);        // one partial-sum plane per bone group
+    p.zpark = park ? 1 : 0;
+    p.off_z = off;   off += round_up((park ? 1 : vr::NG) * p.zcap * 8, 128);   // the job's complex baseband samples (per bone group if !park)
+    p.off_zp = off;  if (park) off += (W / vr::NG) * 2 * vr::NG * 32 * 8;     // per team: two parking buffers of 4 x 32 partial sums
     p.off_o = off;   off += round_up(vr::NFFT * p.ostride * 4, 128);
     p.off_scr = off; off += W * p.scr_bytes;
     p.off_xg = off;  off += (W / vr::NG) * p.xg_bytes;
+    p.off_tab = off; if (ups) off += (W / vr::NG) * (int)sizeof(vr::UpsTab);   // per-team (offset, interval) of the chunk's steps
     p.off_ring = off;
     const int SMEM_SM = 233472, SMEM_CTA_MAX = 232448;
     const int teams = W / vr::NG;
@@ -212,6 +215,7 @@ int make_plan(int64_t N, int64_t T, int V, int M, const int32_t* src, const int3
         S = (budget - off) / p.stage_bytes;
         S = std::min(S, std::min(vr::MAX_STAGES, 3 * teams));
         if (g_tuning.stages > 0) S = std::min(S, g_tuning.stages);
+        if (ups) { if (S >= teams) { S = teams; break; } continue; }    // fused up-sampling: one stage per team, no ring
         if (S >= teams + 1 || (ctas_per_sm == 1 && S >= 2)) break;
     }
     if (ctas_per_sm < 1 || S < 2)
@@ -222,23 +226,49 @@ int make_plan(int64_t N, int64_t T, int V, int M, const int32_t* src, const int3
     return VR_OK;
 }
 
+// Short sequences (one job each) keep one z plane per bone group and sum them once per job.  Long
+// sequences are cut into jobs whose samples fit the z buffer; there a single plane is kept and the four
+// partial sums of a chunk are parked and folded one chunk later.  A larger buffer means less halo
+// (n_fft + 2 chunks of samples are synthesised twice at every cut) but can cost the second resident CTA
+// per SM; two CTAs matter more (the kernel is latency-bound with one), so take the largest buffer that
+// still leaves room for two.
+int make_plan(int64_t N, int64_t T, int V, int M, const int32_t* src, const int32_t* dst, int E,
+              int n_fft, int hop, int img, bool ups, int sm_count, bool x_aligned, vr::Params& p, int& grid, int& ctas_per_sm) {
+    const int want = g_tuning.ctas_per_sm > 0 ? g_tuning.ctas_per_sm : 2;
+    const int caps[] = {2304, 1920, 1664, 1408, 1152};
+    int rc = make_plan_z(N, T, V, M, src, dst, E, n_fft, hop, img, ups, sm_count, x_aligned, caps[0], ups, p, grid, ctas_per_sm);
+    if (rc || (!ups && ctas_per_sm >= want && p.jobs_per_seq == 1)) return rc;
+    for (int zc : caps) {
+        vr::Params q;
+        int g2, c2;
+        if (make_plan_z(N, T, V, M, src, dst, E, n_fft, hop, img, ups, sm_count, x_aligned, zc, true, q, g2, c2) == VR_OK && c2 >= want) {
+            p = q; grid = g2; ctas_per_sm = c2;
+            return VR_OK;
+        }
+    }
+    g_err[0] = 0;
+    return make_plan_z(N, T, V, M, src, dst, E, n_fft, hop, img, ups, sm_count, x_aligned, caps[0], true, p, grid, ctas_per_sm);
+}
+
 // kernel variants: range rounding mode x compile-time V*M (plane stride as an immediate); VM=0 is generic
 typedef void (*KernelFn)(const vr::Params);
-struct Variant { bool fma; int vm; int nb; KernelFn fn; };
-#define VR_VARIANT(VM, NB) {false, VM, NB, vr::vr_fused_kernel<false, VM, NB>}, {true, VM, NB, vr::vr_fused_kernel<true, VM, NB>}
+struct Variant { bool fma; int vm; int nb; bool ups; bool park; KernelFn fn; };
+#define VR_VARIANT(VM, NB, UPS, PARK) {false, VM, NB, UPS, PARK, vr::vr_fused_kernel<false, VM, NB, UPS, PARK>}, \
+                                      {true, VM, NB, UPS, PARK, vr::vr_fused_kernel<true, VM, NB, UPS, PARK>}
 const Variant kVariants[] = {
-    VR_VARIANT(0, 1), VR_VARIANT(0, 2),     // generic V*M: one body at a time / two bodies at a time (M even)
-    VR_VARIANT(50, 2),                      // NTU, two bodies
-    VR_VARIANT(25, 1),                      // NTU, one body
-    VR_VARIANT(17, 1),                      // simulated gait
-    VR_VARIANT(42, 1),                      // CMU mocap markers
+    // short sequences (one job each, a z plane per bone group): generic V*M, one / two bodies at a time; NTU
+    VR_VARIANT(0, 1, false, false), VR_VARIANT(0, 2, false, false), VR_VARIANT(50, 2, false, false),
+    // long sequences (several jobs, parked partial sums)
+    VR_VARIANT(0, 1, false, true), VR_VARIANT(0, 2, false, true), VR_VARIANT(50, 2, false, true),
+    // fused temporal up-sampling (always long)
+    VR_VARIANT(0, 1, true, true), VR_VARIANT(0, 2, true, true), VR_VARIANT(50, 2, true, true),
 };
 const int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
-KernelFn pick_kernel(bool fma, int vm, int m) {
+KernelFn pick_kernel(bool fma, int vm, int m, bool ups, bool park) {
     const int nb = (m % 2 == 0) ? 2 : 1;
     KernelFn generic = nullptr;
     for (int i = 0; i < kNumVariants; ++i) {
-        if (kVariants[i].fma != fma || kVariants[i].nb != nb) continue;
+        if (kVariants[i].fma != fma || kVariants[i].nb != nb || kVariants[i].ups != ups || kVariants[i].park != park) continue;
         if (kVariants[i].vm == vm) return kVariants[i].fn;
         if (kVariants[i].vm == 0) generic = kVariants[i].fn;
     }
@@ -274,7 +304,7 @@ struct PlanCache {
     bool valid = false;
     int64_t N = 0, T = 0;
     int V = 0, M = 0, E = 0, n_fft = 0, hop = 0, img = 0, sm_count = 0, grid = 0, cps = 0;
-    bool aligned = false;
+    bool aligned = false, ups = false;
     Tuning tuning;
     std::vector<int32_t> src, dst;
     vr::Params p;
@@ -282,9 +312,9 @@ struct PlanCache {
 thread_local PlanCache t_plan;
 
 int cached_plan(int64_t N, int64_t T, int V, int M, const int32_t* src, const int32_t* dst, int E,
-                int n_fft, int hop, int img, int sm_count, bool aligned, vr::Params& p, int& grid, int& cps) {
+                int n_fft, int hop, int img, bool ups, int sm_count, bool aligned, vr::Params& p, int& grid, int& cps) {
     PlanCache& c = t_plan;
-    if (c.valid && c.N == N && c.T == T && c.V == V && c.M == M && c.E == E && c.n_fft == n_fft && c.hop == hop && c.img == img &&
+    if (c.valid && c.N == N && c.T == T && c.V == V && c.M == M && c.E == E && c.n_fft == n_fft && c.hop == hop && c.img == img && c.ups == ups &&
         c.sm_count == sm_count && c.aligned == aligned && src && dst &&
         c.tuning.warps == g_tuning.warps && c.tuning.ctas_per_sm == g_tuning.ctas_per_sm && c.tuning.stages == g_tuning.stages &&
         memcmp(c.src.data(), src, sizeof(int32_t) * E) == 0 && memcmp(c.dst.data(), dst, sizeof(int32_t) * E) == 0) {
@@ -292,9 +322,9 @@ int cached_plan(int64_t N, int64_t T, int V, int M, const int32_t* src, const in
         return VR_OK;
     }
     c.valid = false;
-    int rc = make_plan(N, T, V, M, src, dst, E, n_fft, hop, img, sm_count, aligned, p, grid, cps);
+    int rc = make_plan(N, T, V, M, src, dst, E, n_fft, hop, img, ups, sm_count, aligned, p, grid, cps);
     if (rc) return rc;
-    c.N = N; c.T = T; c.V = V; c.M = M; c.E = E; c.n_fft = n_fft; c.hop = hop; c.img = img; c.sm_count = sm_count; c.aligned = aligned;
+    c.N = N; c.T = T; c.V = V; c.M = M; c.E = E; c.n_fft = n_fft; c.hop = hop; c.img = img; c.ups = ups; c.sm_count = sm_count; c.aligned = aligned;
     c.tuning = g_tuning;
     c.src.assign(src, src + E); c.dst.assign(dst, dst + E);
     c.p = p; c.grid = grid; c.cps = cps; c.valid = true;
@@ -303,7 +333,10 @@ int cached_plan(int64_t N, int64_t T, int V, int M, const int32_t* src, const in
 
 int launch(const float* x, int64_t N, int64_t T, int V, int M, const int32_t* src, const int32_t* dst, int E,
            const float* lam_dev, const float* loc_dev, float lam_val, const float* loc_val,
-           int n_fft, int hop, uint32_t flags, int img, float* out, float* iq, cudaStream_t stream) {
+           int n_fft, int hop, uint32_t flags, int img, float* out, float* iq, cudaStream_t stream,
+           const double* coef = nullptr, int ups_T = 0, int ups_K = 0) {
+    // coef != nullptr: fused temporal up-sampling; T is then the UP-SAMPLED length ups_K * ups_T and x is only
+    // used for its alignment (the kernel reads the spline coefficients instead)
     if (!x || !out) return fail(VR_ERR_ARG, "x and out must not be null");
     if ((lam_dev == nullptr) != (loc_dev == nullptr)) return fail(VR_ERR_ARG, "wavelength and radar_location must both be device pointers or both be null");
     if (flags & ~VR_FLAG_RANGE_FMA) return fail(VR_ERR_ARG, "unknown flags 0x%x", flags);
@@ -312,9 +345,11 @@ int launch(const float* x, int64_t N, int64_t T, int V, int M, const int32_t* sr
     if (rc) return rc;
     vr::Params p;
     int grid, cps;
-    rc = cached_plan(N, T, V, M, src, dst, E, n_fft, hop, img, sm_count, ((uintptr_t)x & 15) == 0, p, grid, cps);
+    rc = cached_plan(N, T, V, M, src, dst, E, n_fft, hop, img, coef != nullptr, sm_count, ((uintptr_t)x & 15) == 0, p, grid, cps);
     if (rc) return rc;
     p.x = x; p.out = out; p.iq = iq; p.tl = g_timeline;
+    p.coef = coef; p.ups_T = ups_T; p.ups_K = ups_K;
+    p.ups_ratio = coef ? (double)(ups_T - 1) / (double)((long long)ups_K * ups_T - 1) : 0.0;
     p.lam_ptr = lam_dev; p.loc_ptr = loc_dev;
     p.lam_val = lam_val;
     if (loc_val) { p.loc_val[0] = loc_val[0]; p.loc_val[1] = loc_val[1]; p.loc_val[2] = loc_val[2]; }
@@ -328,7 +363,7 @@ int launch(const float* x, int64_t N, int64_t T, int V, int M, const int32_t* sr
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, pick_kernel((flags & VR_FLAG_RANGE_FMA) != 0, p.VM, p.M), p));
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, pick_kernel((flags & VR_FLAG_RANGE_FMA) != 0, p.VM, p.M, coef != nullptr, p.zpark != 0), p));
     return VR_OK;
 }
 
@@ -391,7 +426,7 @@ int vr_plan_image(int64_t N, int64_t T, int32_t V, int32_t M, const int32_t* src
     if (!plan) return fail(VR_ERR_ARG, "plan must not be null");
     vr::Params p;
     int grid, cps;
-    int rc = make_plan(N, T, V, M, src_host, dst_host, E, n_fft, hop, image_size, sm_count > 0 ? sm_count : 148, true, p, grid, cps);
+    int rc = make_plan(N, T, V, M, src_host, dst_host, E, n_fft, hop, image_size, false, sm_count > 0 ? sm_count : 148, true, p, grid, cps);
     if (rc) return rc;
     plan[0] = grid; plan[1] = (p.W + 1) * 32; plan[2] = p.smem_bytes; plan[3] = p.S; plan[4] = p.FJ;
     plan[5] = p.jobs_per_seq; plan[6] = p.FB; plan[7] = p.tma_in; plan[8] = p.bulk_out; plan[9] = p.cmax;
@@ -448,9 +483,13 @@ int vr_forward_host_f32(const float* x_host, int64_t N, int64_t T, int32_t V, in
     return VR_OK;
 }
 
-int vr_pad_frames_f32(const float* x_dev, int64_t N, int64_t T, int32_t V, int32_t M, int32_t num_pad_frames,
-                      float sigma, float* out_dev, void* stream) {
-    if (!x_dev || !out_dev) return fail(VR_ERR_ARG, "x_dev and out_dev must not be null");
+}  // extern "C"
+namespace {
+// Dataset.pad_frames on the device.  out_dev: the up-sampled batch, and/or coef_dev: only the spline
+// (per-interval cubics) for the fused radar kernel.
+int pad_launch(const float* x_dev, int64_t N, int64_t T, int32_t V, int32_t M, int32_t num_pad_frames,
+               float sigma, float* out_dev, double* coef_dev, void* stream) {
+    if (!x_dev || (!out_dev && !coef_dev)) return fail(VR_ERR_ARG, "x_dev and out_dev must not be null");
     if (N <= 0 || V <= 0 || M <= 0) return fail(VR_ERR_SHAPE, "N, V, M must be positive (got %lld, %d, %d)", (long long)N, V, M);
     if (T < 4) return fail(VR_ERR_SHAPE, "T=%lld: cubic interpolation needs at least 4 frames (scipy interp1d raises ValueError)", (long long)T);
     if (num_pad_frames < 1) return fail(VR_ERR_SHAPE, "num_pad_frames must be >= 1, got %d", num_pad_frames);
@@ -472,7 +511,7 @@ int vr_pad_frames_f32(const float* x_dev, int64_t N, int64_t T, int32_t V, int32
         for (int i = 0; i <= 2 * p.radius; ++i) sum += phi[i];
         for (int j = 0; j <= p.radius; ++j) p.w[j] = phi[p.radius + j] / sum;
     }
-    p.x = x_dev; p.out = out_dev;
+    p.x = x_dev; p.out = out_dev; p.coef = coef_dev;
     p.planes = N * 3; p.T = (int)T; p.VM = V * M; p.K = num_pad_frames;
     p.ratio = (double)(T - 1) / (double)((long long)num_pad_frames * T - 1);
     // columns per CTA: 12 bytes per (frame, column) + 8 bytes per frame of shared memory
@@ -497,6 +536,43 @@ int vr_pad_frames_f32(const float* x_dev, int64_t N, int64_t T, int32_t V, int32
     vr::vr_pad_frames_kernel<<<grid, 1024, smem, (cudaStream_t)stream>>>(p);
     CUDA_TRY(cudaGetLastError());
     return VR_OK;
+}
+}  // namespace
+extern "C" {
+
+int vr_pad_frames_f32(const float* x_dev, int64_t N, int64_t T, int32_t V, int32_t M, int32_t num_pad_frames,
+                      float sigma, float* out_dev, void* stream) {
+    if (!out_dev) return fail(VR_ERR_ARG, "x_dev and out_dev must not be null");
+    return pad_launch(x_dev, N, T, V, M, num_pad_frames, sigma, out_dev, nullptr, stream);
+}
+
+int64_t vr_upsampled_workspace_bytes(int64_t N, int64_t T, int32_t V, int32_t M) {
+    if (N <= 0 || T < 2 || V <= 0 || M <= 0) return 0;
+    return N * (T - 1) * 4 * 3 * (int64_t)V * M * (int64_t)sizeof(double);
+}
+
+int vr_forward_upsampled_f32(const float* x_dev, int64_t N, int64_t T, int32_t V, int32_t M,
+                             const int32_t* src_host, const int32_t* dst_host, int32_t E,
+                             const float* wavelength_dev, const float* radar_loc_dev,
+                             int32_t n_fft, int32_t hop, uint32_t flags,
+                             int32_t num_pad_frames, float sigma, int32_t image_size,
+                             void* workspace_dev, int64_t workspace_bytes, float* out_dev, void* stream) {
+    if (!wavelength_dev || !radar_loc_dev) return fail(VR_ERR_ARG, "wavelength_dev and radar_loc_dev must not be null");
+    if (!x_dev || !out_dev || !workspace_dev) return fail(VR_ERR_ARG, "x_dev, out_dev and workspace_dev must not be null");
+    if (image_size < 0) return fail(VR_ERR_SHAPE, "image_size must be >= 0, got %d", image_size);
+    if (N <= 0 || V <= 0 || M <= 0) return fail(VR_ERR_SHAPE, "N, V, M must be positive (got %lld, %d, %d)", (long long)N, V, M);
+    if (T < 4) return fail(VR_ERR_SHAPE, "T=%lld: cubic interpolation needs at least 4 frames (scipy interp1d raises ValueError)", (long long)T);
+    if (num_pad_frames < 1) return fail(VR_ERR_SHAPE, "num_pad_frames must be >= 1, got %d", num_pad_frames);
+    if ((double)T * num_pad_frames > (double)(1ll << 30)) return fail(VR_ERR_UNSUPPORTED, "T*num_pad_frames too large");
+    if (workspace_bytes < vr_upsampled_workspace_bytes(N, T, V, M))
+        return fail(VR_ERR_ARG, "workspace of %lld bytes is smaller than vr_upsampled_workspace_bytes = %lld",
+                    (long long)workspace_bytes, (long long)vr_upsampled_workspace_bytes(N, T, V, M));
+    if (((uintptr_t)workspace_dev & 7) != 0) return fail(VR_ERR_ARG, "workspace_dev must be 8-byte aligned");
+    double* coef = static_cast<double*>(workspace_dev);
+    int rc = pad_launch(x_dev, N, T, V, M, num_pad_frames, sigma, nullptr, coef, stream);
+    if (rc) return rc;
+    return launch(x_dev, N, T * num_pad_frames, V, M, src_host, dst_host, E, wavelength_dev, radar_loc_dev, 0.f, nullptr,
+                  n_fft, hop, flags, image_size, out_dev, nullptr, (cudaStream_t)stream, coef, (int)T, num_pad_frames);
 }
 
 int vr_release_host_staging(void) {
@@ -529,7 +605,7 @@ int vr_plan(int64_t N, int64_t T, int32_t V, int32_t M, const int32_t* src_host,
     if (!plan) return fail(VR_ERR_ARG, "plan must not be null");
     vr::Params p;
     int grid, cps;
-    int rc = make_plan(N, T, V, M, src_host, dst_host, E, n_fft, hop, 0, sm_count > 0 ? sm_count : 148, true, p, grid, cps);
+    int rc = make_plan(N, T, V, M, src_host, dst_host, E, n_fft, hop, 0, false, sm_count > 0 ? sm_count : 148, true, p, grid, cps);
     if (rc) return rc;
     plan[0] = grid; plan[1] = (p.W + 1) * 32; plan[2] = p.smem_bytes; plan[3] = p.S; plan[4] = p.FJ;
     plan[5] = p.jobs_per_seq; plan[6] = p.FB; plan[7] = p.tma_in; plan[8] = p.bulk_out; plan[9] = p.cmax;

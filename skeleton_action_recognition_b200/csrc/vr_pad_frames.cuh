@@ -23,7 +23,9 @@ constexpr int PF_MAX_RADIUS = 40;
 
 struct PadParams {
     const float* x;              // (N,3,T,V,M)
-    float* out;                  // (N,3,k*T,V,M)
+    float* out;                  // (N,3,k*T,V,M), or nullptr when only the spline is wanted (coef below)
+    double* coef;                // optional (N, T-1, 4, 3*V*M): the cubic a0..a3 of every input interval and column,
+                                 // consumed by the fused up-sampling + radar kernel (vr_forward_upsampled_f32)
     long long planes;            // N*3
     int T, VM, K, nc, ncb;       // frames in, columns per plane, up-sampling factor, columns per CTA, column blocks per plane
     int radius;
@@ -32,6 +34,27 @@ struct PadParams {
 };
 
 #ifdef __CUDACC__
+// The cubic of input interval [j, j+1] in the local variable tt = s - j (unit sample spacing), from the
+// smoothed samples y and the spline's second derivatives m.  One definition for every kernel that
+// evaluates the spline: value(tt) = fma(tt, fma(tt, fma(tt, a3, a2), a1), a0), rounded to float32.
+__device__ __forceinline__ void pf_cubic(double y0, double y1, double m0, double m1,
+                                         double& a0, double& a1, double& a2, double& a3) {
+    a0 = y0;
+    a1 = (y1 - y0) - (2.0 * m0 + m1) * (1.0 / 6.0);
+    a2 = 0.5 * m0;
+    a3 = (m1 - m0) * (1.0 / 6.0);
+}
+__device__ __forceinline__ float pf_eval(double tt, double a0, double a1, double a2, double a3) {
+    return (float)fma(tt, fma(tt, fma(tt, a3, a2), a1), a0);
+}
+// position of output frame i on the input grid: interval j and offset tt inside it
+__device__ __forceinline__ void pf_locate(long long i, double ratio, int T, int& j, double& tt) {
+    const double s = (double)i * ratio;
+    j = (int)s;
+    j = j > T - 2 ? T - 2 : j;
+    tt = s - (double)j;
+}
+
 __device__ __forceinline__ int pf_reflect(int t, int T) {     // scipy 'reflect': d c b a | a b c d | d c b a
     while (t < 0 || t >= T) t = t < 0 ? -t - 1 : 2 * T - t - 1;
     return t;
@@ -99,30 +122,39 @@ __global__ void __launch_bounds__(1024, 1) vr_pad_frames_kernel(const __grid_con
         }
         __syncthreads();
 
+        // (2b) spline-only mode: hand the per-interval cubics to the fused radar kernel
+        if (p.coef) {
+            const int C3 = 3 * p.VM;
+            const long long n = plane / 3;
+            const int cplane = (int)(plane - n * 3);
+            double* cf = p.coef + (size_t)n * (T - 1) * 4 * C3 + cplane * p.VM + col0;
+            for (int idx = tid; idx < (T - 1) * ncl; idx += blockDim.x) {
+                const int j = idx / ncl, c = idx - j * ncl;
+                double a0, a1, a2, a3;
+                pf_cubic((double)ys[j * nc + c], (double)ys[(j + 1) * nc + c], Msh[j * nc + c], Msh[(j + 1) * nc + c], a0, a1, a2, a3);
+                double* o = cf + (size_t)j * 4 * C3 + c;
+                o[0] = a0; o[C3] = a1; o[2 * C3] = a2; o[3 * C3] = a3;
+            }
+        }
+
         // (3) evaluate the K*T output frames, float64, and write float32 rows.  The plane's output is one
         // contiguous run when the block holds all columns, so a flat index gives coalesced stores; (row, column)
         // advance incrementally (no divisions) and the cubic of the current input interval is kept in
         // registers while consecutive output frames fall into it (K frames per interval).
-        {
+        if (p.out) {
             const int rows_per_step = (int)blockDim.x / ncl;     // threads beyond rows_per_step * ncl sit this phase out,
             const int c = tid % ncl;                             // so that every thread stays on one column
             int jc = -1;
             double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
             for (long long i = tid / ncl; i < KT && tid < rows_per_step * ncl; i += rows_per_step) {
-                const double s = (double)i * p.ratio;
-                int j = (int)s;
-                j = j > T - 2 ? T - 2 : j;
+                int j;
+                double tt;
+                pf_locate(i, p.ratio, T, j, tt);
                 if (j != jc) {
-                    const double y0 = (double)ys[j * nc + c], y1 = (double)ys[(j + 1) * nc + c];
-                    const double m0 = Msh[j * nc + c], m1 = Msh[(j + 1) * nc + c];
-                    a0 = y0;
-                    a1 = (y1 - y0) - (2.0 * m0 + m1) * (1.0 / 6.0);
-                    a2 = 0.5 * m0;
-                    a3 = (m1 - m0) * (1.0 / 6.0);
+                    pf_cubic((double)ys[j * nc + c], (double)ys[(j + 1) * nc + c], Msh[j * nc + c], Msh[(j + 1) * nc + c], a0, a1, a2, a3);
                     jc = j;
                 }
-                const double tt = s - (double)j;
-                op[i * p.VM + c] = (float)fma(tt, fma(tt, fma(tt, a3, a2), a1), a0);
+                op[i * p.VM + c] = pf_eval(tt, a0, a1, a2, a3);
             }
         }
     }

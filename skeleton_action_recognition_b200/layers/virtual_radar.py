@@ -165,6 +165,42 @@ class VirtualRadar(torch.nn.Module):
         _cabi.check(rc)
         return out
 
+    def forward_upsampled(self, x, num_pad_frames=250, sigma=3, image_size=None):
+        """The data loader's temporal up-sampling fused in front of the layer: x is the RAW
+        (N,3,T,V,M) batch; the result equals `self(pad_frames(x, num_pad_frames, sigma))` -- or
+        `self.forward_image(pad_frames(...), image_size)` when `image_size` is given -- bit for bit,
+        without the `num_pad_frames`-times larger batch ever existing in HBM (C ABI
+        vr_forward_upsampled_f32; replaces reference utils.py:128-140 + layers/virtual_radar.py:79-134
+        [+ models/resnet.py:24-26])."""
+        self._check_input(x)
+        if not x.is_cuda:
+            raise RuntimeError("VirtualRadar (B200) has no CPU path: move x to a CUDA device")
+        lam, loc = self.wavelength, self.radar_location
+        if lam.device != x.device or loc.device != x.device:
+            raise RuntimeError("module parameters are on %s but x is on %s; call .to(x.device)" % (lam.device, x.device))
+        xc = x.contiguous()
+        N, _, T, V, M = xc.shape
+        k = int(num_pad_frames)
+        img = 0 if image_size is None else int(image_size)
+        if image_size is not None and img < 1:
+            raise ValueError("image_size must be positive, got %d" % img)
+        shape = (N, 1, img, img) if img else (N, self.n_fft, (k * T) // self.hop_length + 1)
+        out = torch.empty(shape, dtype=torch.float32, device=x.device)
+        if N == 0:
+            return out
+        L = _cabi.lib()
+        nbytes = int(L.vr_upsampled_workspace_bytes(N, T, V, M))
+        work = torch.empty(max(nbytes, 8) // 8, dtype=torch.float64, device=x.device)
+        with torch.cuda.device(x.device):
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            # the up-sampled tensor the reference's loader builds is standard-contiguous: range rounding mode "seq"
+            rc = L.vr_forward_upsampled_f32(xc.data_ptr(), N, T, V, M, self._src_c, self._dst_c, len(self.src),
+                                            lam.data_ptr(), loc.data_ptr(), self.n_fft, self.hop_length, 0,
+                                            k, ctypes.c_float(float(sigma)), img, work.data_ptr(), nbytes,
+                                            out.data_ptr(), ctypes.c_void_p(stream))
+        _cabi.check(rc)
+        return out
+
     def forward_debug(self, x):
         """forward plus the intermediate complex baseband signal (N,T,2); for stage-level parity tests."""
         self._check_input(x)
