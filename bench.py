@@ -404,10 +404,17 @@ def main():
                "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__),
                "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)]
         sys.exit(subprocess.call(cmd))
+    # exactly ONE line on stdout: libraries (NCCL's version banner, torch warnings) write to fd 1 too, so
+    # everything except the final JSON line is sent to stderr
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:
         run_ours(args, rank, world, local_rank)
+    real_stdout.flush()
 
 
 if __name__ == "__main__":

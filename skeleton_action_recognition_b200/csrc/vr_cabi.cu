@@ -4,6 +4,7 @@
 #include "../../include/virtual_radar_b200.h"
 #include "vr_kernels.cuh"
 #include "vr_pad_frames.cuh"
+#include "vr_backward.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -573,6 +574,51 @@ int vr_forward_upsampled_f32(const float* x_dev, int64_t N, int64_t T, int32_t V
     if (rc) return rc;
     return launch(x_dev, N, T * num_pad_frames, V, M, src_host, dst_host, E, wavelength_dev, radar_loc_dev, 0.f, nullptr,
                   n_fft, hop, flags, image_size, out_dev, nullptr, (cudaStream_t)stream, coef, (int)T, num_pad_frames);
+}
+
+int vr_backward_params_f32(const float* x_dev, const float* iq_dev, const float* grad_out_dev,
+                           int64_t N, int64_t T, int32_t V, int32_t M,
+                           const int32_t* src_host, const int32_t* dst_host, int32_t E,
+                           const float* wavelength_dev, const float* radar_loc_dev,
+                           int32_t n_fft, int32_t hop, uint32_t flags,
+                           float* gz_work_dev, double* grad_params_dev, void* stream) {
+    if (!x_dev || !iq_dev || !grad_out_dev || !gz_work_dev || !grad_params_dev || !wavelength_dev || !radar_loc_dev)
+        return fail(VR_ERR_ARG, "device pointers must not be null");
+    if (flags & ~VR_FLAG_RANGE_FMA) return fail(VR_ERR_ARG, "unknown flags 0x%x", flags);
+    if (N <= 0 || T <= 0 || V <= 0 || M <= 0 || hop <= 0) return fail(VR_ERR_SHAPE, "N, T, V, M, hop must be positive");
+    if (n_fft != vr::NFFT) return fail(VR_ERR_UNSUPPORTED, "this ABI version implements n_fft=256 only (got %d)", n_fft);
+    if (T <= n_fft / 2) return fail(VR_ERR_SHAPE, "T=%lld must exceed n_fft/2=%d", (long long)T, n_fft / 2);
+    if (T > (1ll << 30)) return fail(VR_ERR_UNSUPPORTED, "T=%lld too long", (long long)T);
+    if (!src_host || !dst_host) return fail(VR_ERR_ARG, "edge arrays must not be null");
+    if (E <= 0 || E > vr::NG * vr::MAX_EG) return fail(VR_ERR_UNSUPPORTED, "E=%d outside [1, %d]", E, vr::NG * vr::MAX_EG);
+    if (V > 65535) return fail(VR_ERR_UNSUPPORTED, "V=%d too large", V);
+    int dev, sm_count;
+    int rc = device_setup(dev, sm_count);
+    if (rc) return rc;
+    vr::BwdParams p;
+    memset(&p, 0, sizeof(p));
+    for (int e = 0; e < E; ++e) {
+        if (src_host[e] < 0 || src_host[e] >= V || dst_host[e] < 0 || dst_host[e] >= V)
+            return fail(VR_ERR_SHAPE, "edge %d = (%d,%d) indexes a joint outside [0,%d)", e, src_host[e], dst_host[e], V);
+        p.src[e] = (uint16_t)src_host[e]; p.dst[e] = (uint16_t)dst_host[e];
+    }
+    p.x = x_dev; p.iq = iq_dev; p.gout = grad_out_dev; p.gz = gz_work_dev; p.gparams = grad_params_dev;
+    p.lam_ptr = wavelength_dev; p.loc_ptr = radar_loc_dev;
+    p.N = N; p.T = T; p.V = V; p.M = M; p.E = E; p.hop = hop; p.VM = V * M;
+    p.F = (int)(T / hop) + 1;
+    p.fma_range = (flags & VR_FLAG_RANGE_FMA) ? 1 : 0;
+    p.inv_E = 1.0f / (float)E;
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemsetAsync(gz_work_dev, 0, (size_t)N * T * 2 * sizeof(float), st));
+    const long long frames = N * (long long)p.F;
+    const int grid1 = (int)std::min<long long>((frames + vr::BWD_WARPS - 1) / vr::BWD_WARPS, (long long)sm_count * 8);
+    vr::vr_stft_adjoint_kernel<<<grid1, vr::BWD_WARPS * 32, 0, st>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    const long long steps = N * T;
+    const int grid2 = (int)std::min<long long>((steps + 127) / 128, (long long)sm_count * 16);
+    vr::vr_synth_adjoint_kernel<<<grid2, 128, 0, st>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    return VR_OK;
 }
 
 int vr_release_host_staging(void) {

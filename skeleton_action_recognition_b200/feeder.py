@@ -45,7 +45,7 @@ class Dataset(torch.utils.data.Dataset):
         return len(self.data)
 
     def __getitem__(self, index):
-        x = torch.from_numpy(np.ascontiguousarray(self.data[index], dtype=np.float32))
+        x = torch.from_numpy(np.array(self.data[index], dtype=np.float32))     # a writable copy of the memory-mapped sample
         return x, torch.as_tensor(self.labels[index])
 
     def upsample(self, batch):

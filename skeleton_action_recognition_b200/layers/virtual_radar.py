@@ -62,6 +62,38 @@ class _STFTKernels(torch.nn.Module):
                                       "trained STFT kernels are not supported by the CUDA path")
 
 
+class _RadarFunction(torch.autograd.Function):
+    """forward() with gradients for `wavelength` and `radar_location` (the reference gets them from
+    PyTorch autograd over layers/virtual_radar.py:79-134; here: C ABI vr_backward_params_f32).  The
+    forward launch is the same fused kernel, asked to also save the complex baseband signal."""
+
+    @staticmethod
+    def forward(ctx, lam, loc, xc, layer, flags):
+        out, iq = layer._launch(xc, flags, want_iq=True)
+        ctx.save_for_backward(lam, loc, xc, iq)
+        ctx.layer, ctx.flags = layer, flags
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lam, loc, xc, iq = ctx.saved_tensors
+        layer = ctx.layer
+        N, _, T, V, M = xc.shape
+        g = grad_out.contiguous().to(torch.float32)
+        gz = torch.empty((N, T, 2), dtype=torch.float32, device=xc.device)
+        gp = torch.zeros(4, dtype=torch.float64, device=xc.device)
+        with torch.cuda.device(xc.device):
+            stream = torch.cuda.current_stream(xc.device).cuda_stream
+            rc = _cabi.lib().vr_backward_params_f32(xc.data_ptr(), iq.data_ptr(), g.data_ptr(), N, T, V, M,
+                                                    layer._src_c, layer._dst_c, len(layer.src),
+                                                    lam.data_ptr(), loc.data_ptr(), layer.n_fft, layer.hop_length,
+                                                    ctx.flags, gz.data_ptr(), gp.data_ptr(), ctypes.c_void_p(stream))
+        _cabi.check(rc)
+        g_lam = gp[0].to(torch.float32).reshape(lam.shape) if ctx.needs_input_grad[0] else None
+        g_loc = gp[1:4].to(torch.float32).reshape(loc.shape) if ctx.needs_input_grad[1] else None
+        return g_lam, g_loc, None, None, None
+
+
 class VirtualRadar(torch.nn.Module):
     """Skeleton sequences -> micro-Doppler log-spectrograms on a B200 (see module docstring)."""
 
@@ -69,14 +101,15 @@ class VirtualRadar(torch.nn.Module):
                  train_wavelength=False, train_radar_location=False, train_stft_kernel=False,
                  n_fft=256, hop_length=16, device='cuda:0'):
         super().__init__()
-        if train_wavelength or train_radar_location or train_stft_kernel:
-            raise NotImplementedError("the CUDA VirtualRadar is forward-only (SURVEY 8b); the reference's "
-                                      "training script never enables these flags either (main_spectrogram.py:128-136)")
+        if train_stft_kernel:
+            raise NotImplementedError("trainable STFT kernels are not supported: the CUDA path evaluates the Hann-windowed "
+                                      "DFT with an FFT (the reference's training script never enables the flag, "
+                                      "main_spectrogram.py:128-136)")
         _cabi.lib()   # fail at construction time if the extension is missing
         self.wavelength = torch.nn.Parameter(torch.as_tensor(wavelength, dtype=torch.float32),
-                                             requires_grad=False)
+                                             requires_grad=bool(train_wavelength))
         self.radar_location = torch.nn.Parameter(torch.as_tensor(radar_location, dtype=torch.float32),
-                                                 requires_grad=False)
+                                                 requires_grad=bool(train_radar_location))
         self.src, self.dst = map(list, zip(*edges))
         self.stft = _STFTKernels(n_fft, hop_length, False, device)
         self.n_fft = n_fft
@@ -109,13 +142,32 @@ class VirtualRadar(torch.nn.Module):
         if x.dtype != torch.float32:
             raise ValueError("VirtualRadar computes in float32 like the reference; got %s" % x.dtype)
         if x.requires_grad and torch.is_grad_enabled():
-            raise NotImplementedError("the CUDA VirtualRadar is forward-only: x.requires_grad is not supported")
+            raise NotImplementedError("gradients with respect to the skeleton data are not implemented "
+                                      "(wavelength and radar_location are): detach x")
 
     def _prepare(self, x):
         """Pick the range rounding mode from the caller's strides BEFORE normalising the layout
         (ATen's CPU norm rounds differently when the coordinate axis is innermost)."""
         flags = _cabi.VR_FLAG_RANGE_FMA if x.stride(1) == 1 and x.shape[1] > 1 else 0
         return x.contiguous(), flags
+
+    def _launch(self, xc, flags, want_iq=False):
+        N, _, T, V, M = xc.shape
+        out = torch.empty(self.output_shape(xc.shape), dtype=torch.float32, device=xc.device)
+        iq = torch.empty((N, T, 2), dtype=torch.float32, device=xc.device) if want_iq else None
+        if N == 0:
+            return out, iq
+        L = _cabi.lib()
+        with torch.cuda.device(xc.device):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(xc.device).cuda_stream)
+            args = (xc.data_ptr(), N, T, V, M, self._src_c, self._dst_c, len(self.src), self.wavelength.data_ptr(),
+                    self.radar_location.data_ptr(), self.n_fft, self.hop_length, flags, out.data_ptr())
+            rc = L.vr_forward_debug_f32(*args, iq.data_ptr(), stream) if want_iq else L.vr_forward_f32(*args, stream)
+        _cabi.check(rc)
+        return out, iq
+
+    def _needs_grad(self):
+        return torch.is_grad_enabled() and (self.wavelength.requires_grad or self.radar_location.requires_grad)
 
     def forward(self, x):
         self._check_input(x)
@@ -126,17 +178,9 @@ class VirtualRadar(torch.nn.Module):
         if lam.device != x.device or loc.device != x.device:
             raise RuntimeError("module parameters are on %s but x is on %s; call .to(x.device)" % (lam.device, x.device))
         xc, flags = self._prepare(x)
-        N, _, T, V, M = xc.shape
-        out = torch.empty(self.output_shape(xc.shape), dtype=torch.float32, device=x.device)
-        if N == 0:
-            return out
-        with torch.cuda.device(x.device):
-            stream = torch.cuda.current_stream(x.device).cuda_stream
-            rc = _cabi.lib().vr_forward_f32(xc.data_ptr(), N, T, V, M, self._src_c, self._dst_c, len(self.src),
-                                            lam.data_ptr(), loc.data_ptr(), self.n_fft, self.hop_length,
-                                            flags, out.data_ptr(), ctypes.c_void_p(stream))
-        _cabi.check(rc)
-        return out
+        if self._needs_grad() and xc.shape[0] > 0:
+            return _RadarFunction.apply(lam, loc, xc, self, flags)
+        return self._launch(xc, flags)[0]
 
     def forward_image(self, x, image_size=256):
         """The layer fused with its consumer's input stage (reference models/resnet.py:24-26):
@@ -152,6 +196,8 @@ class VirtualRadar(torch.nn.Module):
         image_size = int(image_size)
         if image_size < 1:
             raise ValueError("image_size must be positive, got %d" % image_size)
+        if self._needs_grad():      # trainable radar parameters: differentiable spectrogram, then torch's resize
+            return torch.nn.functional.interpolate(self.forward(x).unsqueeze(1), image_size)
         xc, flags = self._prepare(x)
         N, _, T, V, M = xc.shape
         out = torch.empty((N, 1, image_size, image_size), dtype=torch.float32, device=x.device)
@@ -184,6 +230,10 @@ class VirtualRadar(torch.nn.Module):
         img = 0 if image_size is None else int(image_size)
         if image_size is not None and img < 1:
             raise ValueError("image_size must be positive, got %d" % img)
+        if self._needs_grad():      # trainable radar parameters: materialise the up-sampled batch, differentiable layer
+            from ..upsample import pad_frames
+            up = pad_frames(xc, k, sigma)
+            return self.forward_image(up, img) if img else self.forward(up)
         shape = (N, 1, img, img) if img else (N, self.n_fft, (k * T) // self.hop_length + 1)
         out = torch.empty(shape, dtype=torch.float32, device=x.device)
         if N == 0:
@@ -205,17 +255,7 @@ class VirtualRadar(torch.nn.Module):
         """forward plus the intermediate complex baseband signal (N,T,2); for stage-level parity tests."""
         self._check_input(x)
         xc, flags = self._prepare(x)
-        N, _, T, V, M = xc.shape
-        out = torch.empty(self.output_shape(xc.shape), dtype=torch.float32, device=x.device)
-        iq = torch.empty((N, T, 2), dtype=torch.float32, device=x.device)
-        with torch.cuda.device(x.device):
-            stream = torch.cuda.current_stream(x.device).cuda_stream
-            rc = _cabi.lib().vr_forward_debug_f32(xc.data_ptr(), N, T, V, M, self._src_c, self._dst_c, len(self.src),
-                                                  self.wavelength.data_ptr(), self.radar_location.data_ptr(),
-                                                  self.n_fft, self.hop_length, flags, out.data_ptr(), iq.data_ptr(),
-                                                  ctypes.c_void_p(stream))
-        _cabi.check(rc)
-        return out, iq
+        return self._launch(xc, flags, want_iq=True)
 
     def forward_host(self, x, out=None, sub_batch=0, device=None):
         """End-to-end call on HOST tensors: x (N,3,T,V,M) float32 on the CPU (pinned for full copy

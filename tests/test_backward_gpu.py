@@ -1,0 +1,118 @@
+"""GPU tests of the backward pass for the layer's trainable radar parameters (reference
+layers/virtual_radar.py:40-41, 65-69 + PyTorch autograd over :79-134), through the C ABI
+(vr_backward_params_f32) and torch.autograd.
+
+The phase theta = 4 pi d / lambda is 1e3..1e5 rad, so every term of dL/dlambda carries a factor theta/lambda
+of 1e6..1e8 and the terms cancel heavily.  The parity target is what the reference itself returns: float32
+autograd over the reference's graph (oracle.backward.autograd_grads(dtype=float32), the reference's ops in the
+reference's order).  Tolerance: |gpu - reference_f32| <= 1e-3 * scale, scale = the l2 norm of the per-sequence
+gradients (robust against cancellation in a batch sum).  The distance of both from the float64 graph ("truth")
+is printed and recorded: it is set by the float32 phase and is the same for the reference and for the kernels
+(6e-4 at lambda = 5e-3; 0.3 with the radar 1.5 m away at lambda = 1e-3), and the GPU result must not be further
+from the truth than the reference's own float32 result (x1.5 slack)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import backward as ob
+from tests import fixtures as fx
+
+pytestmark = pytest.mark.gpu
+
+
+def _layer(**kw):
+    from skeleton_action_recognition_b200 import VirtualRadar
+    return VirtualRadar(device="cuda:0", **kw).to("cuda:0")
+
+
+def _truth(x, go, dtype, **kw):
+    gl, gloc = [], []
+    for i in range(x.shape[0]):
+        a, b, _ = ob.autograd_grads(x[i:i + 1], go[i:i + 1], dtype=dtype, **kw)
+        gl.append(a)
+        gloc.append(b)
+    return np.array(gl), np.array(gloc)
+
+
+@pytest.mark.parametrize("kw", [dict(wavelength=5e-3), dict(wavelength=1e-3, radar_location=[0.3, -0.2, 1.5]),
+                                dict(wavelength=5e-4)])
+def test_parameter_gradients_vs_float64_autograd(kw):
+    x = fx.s3_smooth(4, T=300)
+    g = torch.Generator().manual_seed(5)
+    go = torch.randn(4, 256, 19, generator=g)
+    t_lam, t_loc = _truth(x, go.numpy(), torch.float64, **kw)
+    r_lam, r_loc = _truth(x, go.numpy(), torch.float32, **kw)
+    layer = _layer(train_wavelength=True, train_radar_location=True, **kw)
+    assert layer.wavelength.requires_grad and layer.radar_location.requires_grad
+    got_lam, got_loc = [], []
+    for i in range(4):                                   # per-sequence gradients
+        layer.zero_grad()
+        out = layer(x[i:i + 1].cuda())
+        (out * go[i:i + 1].cuda()).sum().backward()
+        got_lam.append(float(layer.wavelength.grad))
+        got_loc.append(layer.radar_location.grad.cpu().numpy().astype(np.float64))
+    got_lam, got_loc = np.array(got_lam), np.array(got_loc)
+    s_lam, s_loc = np.linalg.norm(t_lam), np.linalg.norm(t_loc)
+    e_lam, e_loc = np.abs(got_lam - t_lam).max() / s_lam, np.abs(got_loc - t_loc).max() / s_loc
+    ref_lam, ref_loc = np.abs(r_lam - t_lam).max() / s_lam, np.abs(r_loc - t_loc).max() / s_loc
+    d_lam, d_loc = np.abs(got_lam - r_lam).max() / s_lam, np.abs(got_loc - r_loc).max() / s_loc
+    print("dlambda: gpu vs reference-f32 %.2e | vs truth-f64 %.2e (reference-f32 vs truth %.2e);  dloc: %.2e | %.2e (%.2e)"
+          % (d_lam, e_lam, ref_lam, d_loc, e_loc, ref_loc))
+    assert d_lam <= 1e-3 and d_loc <= 1e-3, (d_lam, d_loc)
+    assert e_lam <= 1.5 * ref_lam + 1e-5 and e_loc <= 1.5 * ref_loc + 1e-5, (e_lam, ref_lam, e_loc, ref_loc)
+    # the batch gradient is the sum of the per-sequence gradients
+    layer.zero_grad()
+    (layer(x.cuda()) * go.cuda()).sum().backward()
+    assert abs(float(layer.wavelength.grad) - got_lam.sum()) <= 1e-5 * np.abs(got_lam).sum()
+
+
+def test_against_the_analytic_restatement_on_the_saved_signal():
+    """Stage level: dL/d(iq) of the adjoint STFT equals the numpy restatement applied to the GPU's own iq."""
+    import ctypes
+    from skeleton_action_recognition_b200 import _cabi
+    x = fx.s1_iid(3, seed=9)
+    g = torch.Generator().manual_seed(6)
+    go = torch.randn(3, 256, 19, generator=g)
+    layer = _layer(wavelength=5e-4)
+    xg = x.cuda()
+    out, iq = layer.forward_debug(xg)
+    gz = torch.empty(3, 300, 2, device="cuda")
+    gp = torch.zeros(4, dtype=torch.float64, device="cuda")
+    gog = go.cuda()
+    rc = _cabi.lib().vr_backward_params_f32(xg.data_ptr(), iq.data_ptr(), gog.data_ptr(), 3, 300, 25, 2,
+                                            layer._src_c, layer._dst_c, 24, layer.wavelength.data_ptr(),
+                                            layer.radar_location.data_ptr(), 256, 16, 0, gz.data_ptr(), gp.data_ptr(),
+                                            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _cabi.check(rc)
+    want = ob.stft_adjoint(iq.cpu().numpy(), go.numpy())
+    got = gz.cpu().numpy().astype(np.float64)
+    assert np.abs(got - want).max() <= 2e-5 * np.abs(want).max()
+
+
+def test_training_step_moves_the_parameters():
+    x = fx.s3_smooth(8, T=300).cuda()
+    layer = _layer(wavelength=1e-3, train_wavelength=True, train_radar_location=True)
+    opt = torch.optim.SGD(layer.parameters(), lr=1e-12)
+    before = (float(layer.wavelength.detach()), layer.radar_location.detach().clone())
+    loss = layer(x).square().mean()
+    loss.backward()
+    assert torch.isfinite(layer.wavelength.grad) and torch.isfinite(layer.radar_location.grad).all()
+    assert layer.stft.wsin.grad is None
+    opt.step()
+    assert float(layer.wavelength.detach()) != before[0]
+    # only one of the two trainable
+    layer2 = _layer(wavelength=1e-3, train_radar_location=True)
+    layer2(x).sum().backward()
+    assert layer2.wavelength.grad is None and layer2.radar_location.grad is not None
+    # composed paths stay differentiable
+    layer.zero_grad()
+    layer.forward_image(x, 64).sum().backward()
+    assert layer.wavelength.grad is not None
+    # no_grad keeps the plain launch
+    with torch.no_grad():
+        assert not layer(x).requires_grad
+    with pytest.raises(NotImplementedError):
+        layer(x.clone().requires_grad_(True))
+    with pytest.raises(NotImplementedError):
+        from skeleton_action_recognition_b200 import VirtualRadar
+        VirtualRadar(train_stft_kernel=True)

@@ -131,7 +131,10 @@ def test_module_surface_matches_reference():
     with pytest.raises(ValueError):
         layer(torch.zeros(1, 2, 300, 25, 2))
     with pytest.raises(NotImplementedError):
-        VirtualRadar(train_wavelength=True, device="cpu")
+        VirtualRadar(train_stft_kernel=True, device="cpu")
+    trainable = VirtualRadar(train_wavelength=True, train_radar_location=True, device="cpu")   # reference flags, :40-41
+    assert trainable.wavelength.requires_grad and trainable.radar_location.requires_grad
+    assert not trainable.stft.wsin.requires_grad
     import copy, pickle
     c = copy.deepcopy(layer)
     assert c.src == layer.src

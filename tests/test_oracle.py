@@ -167,3 +167,17 @@ def test_resize_restatement_full_image():
         ref = torch.nn.functional.interpolate(spec.unsqueeze(1), size).numpy()
         assert np.array_equal(resize.resize_nearest(spec.numpy(), size), ref)
     assert len(resize.kept_frames(4688, 256)) == 256 and len(resize.kept_frames(19, 256)) == 19
+
+
+# ---- gradients of the radar parameters (layers/virtual_radar.py:40-41, 65-69) ---------------------
+@pytest.mark.parametrize("loc", [(0., 0., 0.), (0.3, -0.2, 1.5)])
+def test_analytic_gradients_match_autograd_of_the_reference_graph(loc):
+    from oracle import backward as ob
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(2, 3, 200, 25, 2, generator=g) * 0.3
+    go = torch.randn(2, 256, 200 // 16 + 1, generator=g).numpy()
+    kw = dict(wavelength=5e-3, radar_location=loc)
+    gl_a, gloc_a, _ = ob.autograd_grads(x, go, **kw)
+    gl_n, gloc_n, _ = ob.analytic_grads(x.numpy(), go, **kw)
+    assert abs(gl_n - gl_a) <= 1e-7 * abs(gl_a), (gl_n, gl_a)
+    assert np.allclose(gloc_n, gloc_a, rtol=1e-6, atol=1e-7 * np.abs(gloc_a).max()), (gloc_n, gloc_a)
