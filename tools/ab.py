@@ -1,4 +1,4 @@
-"""A/B timing aid (not a test): python tests/_ab.py lib1.so lib2.so ...  -- times vr_forward_f32 of each library
+"""A/B timing aid (not a test): python tools/ab.py lib1.so lib2.so ...  -- times vr_forward_f32 of each library
 (plain ctypes, only the symbols every version has) on the same box, interleaved, N=256 and N=16384."""
 import ctypes, sys
 import torch

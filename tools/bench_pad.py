@@ -1,4 +1,4 @@
-"""Profiling aid (not a test): throughput of the GPU pad_frames pre-stage.  python tests/_bench_pad.py [N] [k]"""
+"""Profiling aid (not a test): throughput of the GPU pad_frames pre-stage.  python tools/bench_pad.py [N] [k]"""
 import sys, time; sys.path.insert(0, '.')
 import torch
 from skeleton_action_recognition_b200 import pad_frames

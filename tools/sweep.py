@@ -1,4 +1,4 @@
-"""Tuning sweep (not a test): python tests/_sweep.py <lib> [warps ctas_per_sm stages]  -- device-timed via bench-like loop"""
+"""Tuning sweep (not a test): python tools/sweep.py <lib> [warps ctas_per_sm stages]  -- device-timed via bench-like loop"""
 import os, sys, ctypes
 lib = sys.argv[1]
 W, C, S = (int(v) for v in sys.argv[2:5]) if len(sys.argv) > 4 else (0, 0, 0)

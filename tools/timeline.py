@@ -1,4 +1,4 @@
-"""Profiling aid (not a test): per-CTA timeline of one launch.  python tests/_timeline.py [N]"""
+"""Profiling aid (not a test): per-CTA timeline of one launch.  python tools/timeline.py [N]"""
 import sys; sys.path.insert(0, '.')
 import numpy as np, torch
 from skeleton_action_recognition_b200 import VirtualRadar, _cabi
