@@ -116,14 +116,22 @@ int vr_forward_upsampled_f32(const float* x_dev, int64_t N, int64_t T, int32_t V
                              int32_t num_pad_frames, float sigma, int32_t image_size,
                              void* workspace_dev, int64_t workspace_bytes, float* out_dev, void* stream);
 
-/* Backward pass for the layer's two radar parameters (the constructor's train_wavelength /
+/* Backward pass: gradients of the layer's two radar parameters (the constructor's train_wavelength /
  * train_radar_location flags, reference layers/virtual_radar.py:40-41, 65-69; in the reference PyTorch
  * autograd differentiates forward()).  Inputs: the forward's x, the complex baseband signal the forward
  * saved (iq_dev, (N,T,2), from vr_forward_debug_f32) and grad_out_dev (N, n_fft, T/hop+1) = dL/d(out).
  * gz_work_dev: (N,T,2) float32 scratch (zeroed here; holds dL/d(iq) on return).  grad_params_dev: 4
  * float64 values ACCUMULATED (+=) with [dL/dwavelength, dL/dradar_location[0..2]]; the caller zeroes
- * them.  Two launches on `stream`: adjoint STFT (FFT, log-magnitude and fftshift backward, inverse
+ * them.  grad_x_dev (optional): gradient with respect to the skeleton data.  Two launches on `stream`: adjoint STFT (FFT, log-magnitude and fftshift backward, inverse
  * FFT, overlap-add through the reflect padding) and adjoint synthesis (float64 accumulation).        */
+int vr_backward_f32(const float* x_dev, const float* iq_dev, const float* grad_out_dev,
+                    int64_t N, int64_t T, int32_t V, int32_t M,
+                    const int32_t* src_host, const int32_t* dst_host, int32_t E,
+                    const float* wavelength_dev, const float* radar_loc_dev,
+                    int32_t n_fft, int32_t hop, uint32_t flags,
+                    float* gz_work_dev, double* grad_params_dev,
+                    float* grad_x_dev /* (N,3,T,V,M) dL/dx, overwritten; NULL = not wanted */, void* stream);
+/* the same without dL/dx */
 int vr_backward_params_f32(const float* x_dev, const float* iq_dev, const float* grad_out_dev,
                            int64_t N, int64_t T, int32_t V, int32_t M,
                            const int32_t* src_host, const int32_t* dst_host, int32_t E,

@@ -17,15 +17,19 @@ from . import virtual_radar_oracle as vro
 
 
 def autograd_grads(x, grad_out, edges=vro.NTU_EDGES, wavelength=1e-3, radar_location=(0., 0., 0.),
-                   n_fft=256, hop_length=16, dtype=torch.float64):
+                   n_fft=256, hop_length=16, dtype=torch.float64, wrt_x=False):
+    """-> (dL/dwavelength, dL/dradar_location, out) or, with wrt_x, (.., .., dL/dx)."""
     o = vro.OracleVirtualRadar(edges, wavelength, radar_location, n_fft, hop_length, dtype)
     lam = o.wavelength.clone().requires_grad_(True)
     loc = o.radar_location.clone().requires_grad_(True)
-    iq = vro.synthesize_iq(x.to(dtype), o.src, o.dst, loc, lam, "aten")
+    xx = x.to(dtype).clone().requires_grad_(wrt_x)
+    iq = vro.synthesize_iq(xx, o.src, o.dst, loc, lam, "aten")
     out = vro.stft_logmag(iq, o.stft, n_fft)
     loss = (out * torch.as_tensor(grad_out).to(dtype)).sum()
-    g_lam, g_loc = torch.autograd.grad(loss, (lam, loc))
-    return float(g_lam), g_loc.numpy().astype(np.float64), out.detach().numpy()
+    grads = torch.autograd.grad(loss, (lam, loc, xx) if wrt_x else (lam, loc))
+    if wrt_x:
+        return float(grads[0]), grads[1].numpy().astype(np.float64), grads[2].numpy().astype(np.float64)
+    return float(grads[0]), grads[1].numpy().astype(np.float64), out.detach().numpy()
 
 
 def _reflect(t, T):
@@ -55,7 +59,7 @@ def stft_adjoint(iq, grad_out, n_fft=256, hop=16):
 
 
 def analytic_grads(x, grad_out, edges=vro.NTU_EDGES, wavelength=1e-3, radar_location=(0., 0., 0.),
-                   n_fft=256, hop_length=16):
+                   n_fft=256, hop_length=16, wrt_x=False):
     x64 = np.asarray(x, np.float64)
     lam = float(np.float32(wavelength))
     L = np.asarray(np.float32(radar_location), np.float64)[None, :, None, None, None]
@@ -84,4 +88,18 @@ def analytic_grads(x, grad_out, edges=vro.NTU_EDGES, wavelength=1e-3, radar_loca
         kamp = (damp * (-K * 2 * u * (c - 1) / den ** 2))[:, None]
         dudA = np.where(na[:, None] > 0, B / q[:, None] - (dot * nb / (na * q ** 2))[:, None] * A, 0)
     g_loc = (kth * (L - S) + kamp * dudA).sum((0, 2, 3, 4))
-    return float(g_lam), g_loc, iq
+    if not wrt_x:
+        return float(g_lam), g_loc, iq
+    # dL/dx: through the range (S), the aspect cosine (A = L - (S+D)/2, B = D - S) and the mean bone length
+    with np.errstate(divide="ignore", invalid="ignore"):
+        dudB = np.where(nb[:, None] > 0, A / q[:, None] - (dot * na / (nb * q ** 2))[:, None] * B, 0)
+        unitB = np.where(nb[:, None] > 0, B / nb[:, None], 0)
+    G_c = (damp * np.sqrt(np.pi) * (1 / den - 2 * c * u ** 2 / den ** 2)).sum(2, keepdims=True)     # (N,T,1,M)
+    gB = kamp * dudB + (G_c / len(src))[:, None] * unitB
+    gS = kth * (S - L) - 0.5 * kamp * dudA - gB
+    gD = -0.5 * kamp * dudA + gB
+    gx = np.zeros_like(x64)
+    for e, (si, di) in enumerate(zip(src, dst)):
+        gx[:, :, :, si] += gS[:, :, :, e]
+        gx[:, :, :, di] += gD[:, :, :, e]
+    return float(g_lam), g_loc, gx

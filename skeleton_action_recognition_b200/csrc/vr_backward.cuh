@@ -7,7 +7,7 @@
 //                            -> dL/dz (N, T, 2): per frame, X = FFT(hann * zp); G = g * X / (|X| (|X| + 1e-6))
 //                            (log-magnitude and fftshift, :126-133); dL/dzp = hann * conj(FFT(conj(G))) (the
 //                            adjoint of the windowed DFT, :124-125); overlap-add through the reflect padding.
-//   vr_synth_adjoint_kernel  dL/dz and x -> dL/dwavelength, dL/dradar_location: per (sequence, time step, body,
+//   vr_synth_adjoint_kernel  dL/dz and x -> dL/dwavelength, dL/dradar_location (and, on request, dL/dx): per (sequence, time step, body,
 //                            bone) the forward geometry is recomputed (range and phase with the forward's exact
 //                            float32 rounding, the rest in float64) and the analytic derivatives of
 //                            z = sum amp * exp(j theta) are accumulated in float64.
@@ -26,6 +26,7 @@ struct BwdParams {
     const float* gout;           // (N,256,F)
     float* gz;                   // (N,T,2) work buffer, zeroed before the adjoint STFT
     double* gparams;             // [dL/dlambda, dL/dLx, dL/dLy, dL/dLz], accumulated with atomics
+    float* gx;                   // optional dL/dx (N,3,T,V,M), zeroed before the launch; nullptr = not wanted
     const float* lam_ptr;
     const float* loc_ptr;
     long long N, T;
@@ -174,6 +175,8 @@ __global__ void __launch_bounds__(128) vr_synth_adjoint_kernel(const __grid_cons
             if (sumB == 0.f) continue;                                    // absent body: contributes exactly 0
             const double cbar = (double)__fmul_rn(sumB, p.inv_E);
             const double c = cbar * cbar, K = sqrt(PI) * cbar;
+            float* gx0 = p.gx ? p.gx + (n * 3 * T + t) * (long long)p.VM : nullptr;   // this thread's own rows of dL/dx
+            double G_c = 0.0;                                              // dL/d(mean bone length), over this body's bones
             for (int e = 0; e < p.E; ++e) {
                 const float* s = x0 + p.src[e] * p.M + m;
                 const float* d = x0 + p.dst[e] * p.M + m;
@@ -197,14 +200,48 @@ __global__ void __launch_bounds__(128) vr_synth_adjoint_kernel(const __grid_cons
                 const double dL_dth = amp * (gQ * cs - gI * sn);
                 const double dL_damp = gI * cs + gQ * sn;
                 g_lam += dL_dth * (-(double)th / (double)lam);
+                double gsx = 0.0, gsy = 0.0, gsz = 0.0, gdx = 0.0, gdy = 0.0, gdz = 0.0;   // dL/dS, dL/dD of this bone
                 if (rng > 0.f) {
                     const double kth = dL_dth * (4.0 * PI / (double)lam) / (double)rng;
                     g_lx += kth * ((double)Lx - sx); g_ly += kth * ((double)Ly - sy); g_lz += kth * ((double)Lz - sz);
+                    gsx = kth * ((double)sx - Lx); gsy = kth * ((double)sy - Ly); gsz = kth * ((double)sz - Lz);
                 }
+                const double kamp = dL_damp * (-K * 2.0 * u * (c - 1.0) / (den * den));
                 if (na > 0.0) {
-                    const double kamp = dL_damp * (-K * 2.0 * u * (c - 1.0) / (den * den));
                     const double r2 = dot * nb / (na * q * q);
-                    g_lx += kamp * (Bx / q - r2 * Ax); g_ly += kamp * (By / q - r2 * Ay); g_lz += kamp * (Bz / q - r2 * Az);
+                    const double ax = kamp * (Bx / q - r2 * Ax), ay = kamp * (By / q - r2 * Ay), az = kamp * (Bz / q - r2 * Az);   // dL/dA
+                    g_lx += ax; g_ly += ay; g_lz += az;
+                    gsx -= 0.5 * ax; gsy -= 0.5 * ay; gsz -= 0.5 * az;
+                    gdx -= 0.5 * ax; gdy -= 0.5 * ay; gdz -= 0.5 * az;
+                }
+                if (gx0) {
+                    if (nb > 0.0) {
+                        const double r3 = dot * na / (nb * q * q);
+                        const double bx = kamp * (Ax / q - r3 * Bx), by = kamp * (Ay / q - r3 * By), bz = kamp * (Az / q - r3 * Bz);  // dL/dB via u
+                        gsx -= bx; gsy -= by; gsz -= bz;
+                        gdx += bx; gdy += by; gdz += bz;
+                    }
+                    G_c += dL_damp * sqrt(PI) * (1.0 / den - 2.0 * c * u * u / (den * den));
+                    float* gs = gx0 + p.src[e] * p.M + m;
+                    float* gd = gx0 + p.dst[e] * p.M + m;
+                    gs[0] += (float)gsx; gs[ps] += (float)gsy; gs[2 * ps] += (float)gsz;
+                    gd[0] += (float)gdx; gd[ps] += (float)gdy; gd[2 * ps] += (float)gdz;
+                }
+            }
+            if (gx0) {                                                     // through the mean bone length (:110-113)
+                for (int e = 0; e < p.E; ++e) {
+                    const float* s = x0 + p.src[e] * p.M + m;
+                    const float* d = x0 + p.dst[e] * p.M + m;
+                    const double Bx = (double)__ldg(d) - __ldg(s), By = (double)__ldg(d + ps) - __ldg(s + ps),
+                                 Bz = (double)__ldg(d + 2 * ps) - __ldg(s + 2 * ps);
+                    const double nb = sqrt(Bx * Bx + By * By + Bz * Bz);
+                    if (nb > 0.0) {
+                        const double kc = G_c * (double)p.inv_E / nb;
+                        float* gs = gx0 + p.src[e] * p.M + m;
+                        float* gd = gx0 + p.dst[e] * p.M + m;
+                        gs[0] -= (float)(kc * Bx); gs[ps] -= (float)(kc * By); gs[2 * ps] -= (float)(kc * Bz);
+                        gd[0] += (float)(kc * Bx); gd[ps] += (float)(kc * By); gd[2 * ps] += (float)(kc * Bz);
+                    }
                 }
             }
         }

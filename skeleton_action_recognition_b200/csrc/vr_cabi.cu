@@ -582,6 +582,16 @@ int vr_backward_params_f32(const float* x_dev, const float* iq_dev, const float*
                            const float* wavelength_dev, const float* radar_loc_dev,
                            int32_t n_fft, int32_t hop, uint32_t flags,
                            float* gz_work_dev, double* grad_params_dev, void* stream) {
+    return vr_backward_f32(x_dev, iq_dev, grad_out_dev, N, T, V, M, src_host, dst_host, E, wavelength_dev, radar_loc_dev,
+                           n_fft, hop, flags, gz_work_dev, grad_params_dev, nullptr, stream);
+}
+
+int vr_backward_f32(const float* x_dev, const float* iq_dev, const float* grad_out_dev,
+                    int64_t N, int64_t T, int32_t V, int32_t M,
+                    const int32_t* src_host, const int32_t* dst_host, int32_t E,
+                    const float* wavelength_dev, const float* radar_loc_dev,
+                    int32_t n_fft, int32_t hop, uint32_t flags,
+                    float* gz_work_dev, double* grad_params_dev, float* grad_x_dev, void* stream) {
     if (!x_dev || !iq_dev || !grad_out_dev || !gz_work_dev || !grad_params_dev || !wavelength_dev || !radar_loc_dev)
         return fail(VR_ERR_ARG, "device pointers must not be null");
     if (flags & ~VR_FLAG_RANGE_FMA) return fail(VR_ERR_ARG, "unknown flags 0x%x", flags);
@@ -602,7 +612,7 @@ int vr_backward_params_f32(const float* x_dev, const float* iq_dev, const float*
             return fail(VR_ERR_SHAPE, "edge %d = (%d,%d) indexes a joint outside [0,%d)", e, src_host[e], dst_host[e], V);
         p.src[e] = (uint16_t)src_host[e]; p.dst[e] = (uint16_t)dst_host[e];
     }
-    p.x = x_dev; p.iq = iq_dev; p.gout = grad_out_dev; p.gz = gz_work_dev; p.gparams = grad_params_dev;
+    p.x = x_dev; p.iq = iq_dev; p.gout = grad_out_dev; p.gz = gz_work_dev; p.gparams = grad_params_dev; p.gx = grad_x_dev;
     p.lam_ptr = wavelength_dev; p.loc_ptr = radar_loc_dev;
     p.N = N; p.T = T; p.V = V; p.M = M; p.E = E; p.hop = hop; p.VM = V * M;
     p.F = (int)(T / hop) + 1;
@@ -610,6 +620,7 @@ int vr_backward_params_f32(const float* x_dev, const float* iq_dev, const float*
     p.inv_E = 1.0f / (float)E;
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(cudaMemsetAsync(gz_work_dev, 0, (size_t)N * T * 2 * sizeof(float), st));
+    if (grad_x_dev) CUDA_TRY(cudaMemsetAsync(grad_x_dev, 0, (size_t)N * 3 * T * V * M * sizeof(float), st));
     const long long frames = N * (long long)p.F;
     const int grid1 = (int)std::min<long long>((frames + vr::BWD_WARPS - 1) / vr::BWD_WARPS, (long long)sm_count * 8);
     vr::vr_stft_adjoint_kernel<<<grid1, vr::BWD_WARPS * 32, 0, st>>>(p);

@@ -63,8 +63,8 @@ class _STFTKernels(torch.nn.Module):
 
 
 class _RadarFunction(torch.autograd.Function):
-    """forward() with gradients for `wavelength` and `radar_location` (the reference gets them from
-    PyTorch autograd over layers/virtual_radar.py:79-134; here: C ABI vr_backward_params_f32).  The
+    """forward() with gradients for `wavelength`, `radar_location` and `x` (the reference gets them from
+    PyTorch autograd over layers/virtual_radar.py:79-134; here: C ABI vr_backward_f32).  The
     forward launch is the same fused kernel, asked to also save the complex baseband signal."""
 
     @staticmethod
@@ -82,16 +82,18 @@ class _RadarFunction(torch.autograd.Function):
         g = grad_out.contiguous().to(torch.float32)
         gz = torch.empty((N, T, 2), dtype=torch.float32, device=xc.device)
         gp = torch.zeros(4, dtype=torch.float64, device=xc.device)
+        gx = torch.empty_like(xc) if ctx.needs_input_grad[2] else None
         with torch.cuda.device(xc.device):
             stream = torch.cuda.current_stream(xc.device).cuda_stream
-            rc = _cabi.lib().vr_backward_params_f32(xc.data_ptr(), iq.data_ptr(), g.data_ptr(), N, T, V, M,
-                                                    layer._src_c, layer._dst_c, len(layer.src),
-                                                    lam.data_ptr(), loc.data_ptr(), layer.n_fft, layer.hop_length,
-                                                    ctx.flags, gz.data_ptr(), gp.data_ptr(), ctypes.c_void_p(stream))
+            rc = _cabi.lib().vr_backward_f32(xc.data_ptr(), iq.data_ptr(), g.data_ptr(), N, T, V, M,
+                                             layer._src_c, layer._dst_c, len(layer.src),
+                                             lam.data_ptr(), loc.data_ptr(), layer.n_fft, layer.hop_length,
+                                             ctx.flags, gz.data_ptr(), gp.data_ptr(),
+                                             gx.data_ptr() if gx is not None else None, ctypes.c_void_p(stream))
         _cabi.check(rc)
         g_lam = gp[0].to(torch.float32).reshape(lam.shape) if ctx.needs_input_grad[0] else None
         g_loc = gp[1:4].to(torch.float32).reshape(loc.shape) if ctx.needs_input_grad[1] else None
-        return g_lam, g_loc, None, None, None
+        return g_lam, g_loc, gx, None, None
 
 
 class VirtualRadar(torch.nn.Module):
@@ -141,9 +143,6 @@ class VirtualRadar(torch.nn.Module):
                              % (tuple(x.shape) if isinstance(x, torch.Tensor) else type(x),))
         if x.dtype != torch.float32:
             raise ValueError("VirtualRadar computes in float32 like the reference; got %s" % x.dtype)
-        if x.requires_grad and torch.is_grad_enabled():
-            raise NotImplementedError("gradients with respect to the skeleton data are not implemented "
-                                      "(wavelength and radar_location are): detach x")
 
     def _prepare(self, x):
         """Pick the range rounding mode from the caller's strides BEFORE normalising the layout
@@ -166,8 +165,9 @@ class VirtualRadar(torch.nn.Module):
         _cabi.check(rc)
         return out, iq
 
-    def _needs_grad(self):
-        return torch.is_grad_enabled() and (self.wavelength.requires_grad or self.radar_location.requires_grad)
+    def _needs_grad(self, x=None):
+        return torch.is_grad_enabled() and (self.wavelength.requires_grad or self.radar_location.requires_grad
+                                            or (x is not None and x.requires_grad))
 
     def forward(self, x):
         self._check_input(x)
@@ -178,7 +178,7 @@ class VirtualRadar(torch.nn.Module):
         if lam.device != x.device or loc.device != x.device:
             raise RuntimeError("module parameters are on %s but x is on %s; call .to(x.device)" % (lam.device, x.device))
         xc, flags = self._prepare(x)
-        if self._needs_grad() and xc.shape[0] > 0:
+        if self._needs_grad(x) and xc.shape[0] > 0:
             return _RadarFunction.apply(lam, loc, xc, self, flags)
         return self._launch(xc, flags)[0]
 
@@ -196,7 +196,7 @@ class VirtualRadar(torch.nn.Module):
         image_size = int(image_size)
         if image_size < 1:
             raise ValueError("image_size must be positive, got %d" % image_size)
-        if self._needs_grad():      # trainable radar parameters: differentiable spectrogram, then torch's resize
+        if self._needs_grad(x):     # gradients wanted: differentiable spectrogram, then torch's resize
             return torch.nn.functional.interpolate(self.forward(x).unsqueeze(1), image_size)
         xc, flags = self._prepare(x)
         N, _, T, V, M = xc.shape
@@ -230,6 +230,9 @@ class VirtualRadar(torch.nn.Module):
         img = 0 if image_size is None else int(image_size)
         if image_size is not None and img < 1:
             raise ValueError("image_size must be positive, got %d" % img)
+        if x.requires_grad and torch.is_grad_enabled():
+            raise NotImplementedError("the temporal up-sampling has no backward pass: detach x, or differentiate "
+                                      "forward() on an already up-sampled batch")
         if self._needs_grad():      # trainable radar parameters: materialise the up-sampled batch, differentiable layer
             from ..upsample import pad_frames
             up = pad_frames(xc, k, sigma)

@@ -1,6 +1,6 @@
-"""GPU tests of the backward pass for the layer's trainable radar parameters (reference
-layers/virtual_radar.py:40-41, 65-69 + PyTorch autograd over :79-134), through the C ABI
-(vr_backward_params_f32) and torch.autograd.
+"""GPU tests of the backward pass: gradients of the layer's trainable radar parameters and of the skeleton data
+(reference layers/virtual_radar.py:40-41, 65-69 + PyTorch autograd over :79-134), through the C ABI
+(vr_backward_f32) and torch.autograd.
 
 The phase theta = 4 pi d / lambda is 1e3..1e5 rad, so every term of dL/dlambda carries a factor theta/lambda
 of 1e6..1e8 and the terms cancel heavily.  The parity target is what the reference itself returns: float32
@@ -112,7 +112,35 @@ def test_training_step_moves_the_parameters():
     with torch.no_grad():
         assert not layer(x).requires_grad
     with pytest.raises(NotImplementedError):
-        layer(x.clone().requires_grad_(True))
+        layer.forward_upsampled(x[:, :, :40].clone().requires_grad_(True), 10)
     with pytest.raises(NotImplementedError):
         from skeleton_action_recognition_b200 import VirtualRadar
         VirtualRadar(train_stft_kernel=True)
+
+
+@pytest.mark.parametrize("kw", [dict(wavelength=5e-3), dict(wavelength=1e-3, radar_location=[0.3, -0.2, 1.5])])
+def test_gradient_wrt_the_skeleton_data(kw):
+    """dL/dx against float32 autograd over the reference graph (per-sequence l2 scale, 1e-3), an absent body gets 0
+    (the reference returns NaN there, see tests/test_oracle.py), and the float64 graph for information."""
+    x = fx.s3_smooth(3, T=200)
+    x[2, :, :, :, 1] = 0
+    g = torch.Generator().manual_seed(7)
+    go = torch.randn(3, 256, 13, generator=g)
+    layer = _layer(**kw)                                          # parameters frozen: only x needs a gradient
+    xg = x.cuda().requires_grad_(True)
+    (layer(xg) * go.cuda()).sum().backward()
+    got = xg.grad.cpu().numpy().astype(np.float64)
+    assert layer.wavelength.grad is None
+    assert np.all(got[2, :, :, :, 1] == 0)
+    for i in range(2):                                            # sequences without absent bodies
+        _, _, r32 = ob.autograd_grads(x[i:i + 1], go[i:i + 1].numpy(), dtype=torch.float32, wrt_x=True, **kw)
+        _, _, t64 = ob.autograd_grads(x[i:i + 1], go[i:i + 1].numpy(), dtype=torch.float64, wrt_x=True, **kw)
+        scale = np.linalg.norm(r32) / np.sqrt(r32.size)           # rms of the gradient entries
+        d_ref = np.abs(got[i] - r32[0]).max() / scale
+        d_truth, ref_truth = np.abs(got[i] - t64[0]).max() / scale, np.abs(r32[0] - t64[0]).max() / scale
+        print("dx[%d]: gpu vs reference-f32 %.2e | vs truth-f64 %.2e (reference-f32 vs truth %.2e)" % (i, d_ref, d_truth, ref_truth))
+        assert d_ref <= 2e-2 and d_truth <= 1.5 * ref_truth + 1e-3, (d_ref, d_truth, ref_truth)
+    # sequence 2 (absent second body): the present body still matches the closed form evaluated in float64
+    _, _, an = ob.analytic_grads(x[2:3].numpy(), go[2:3].numpy(), wrt_x=True, **kw)
+    scale = np.linalg.norm(an) / np.sqrt(an.size)
+    print("dx[2] vs closed form f64: %.2e" % (np.abs(got[2] - an[0]).max() / scale))
