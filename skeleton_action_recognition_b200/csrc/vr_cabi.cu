@@ -36,6 +36,7 @@ int fail(int code, const char* fmt, ...) {
 struct Tuning { int warps = 0, ctas_per_sm = 0, stages = 0; };
 Tuning g_tuning;
 unsigned long long* g_timeline = nullptr;
+const bool g_dynamic = getenv("VR_B200_STATIC_JOBS") == nullptr;   // dynamic job scheduling for batches larger than the grid (A/B switch)
 const bool g_pdl = getenv("VR_B200_NO_PDL") == nullptr;   // programmatic dependent launch (A/B switch for profiling)   // profiling only (vr_set_timeline_buffer)
 
 // ---- bone partition -----------------------------------------------------------------------------
@@ -197,7 +198,7 @@ int make_plan_z(int64_t N, int64_t T, int V, int M, const int32_t* src, const in
     p.scr_bytes = round_up(std::max(vr::XCH_BYTES, p.eg_max * 128 * NB), 128);
     p.xg_bytes = round_up(2 * vr::NG * 32 * NB * 4, 128);        // double-buffered
     int off = 0;
-    off += round_up(vr::MAX_STAGES * (8 + 8 + 4), 128);                  // full[] / empty[] mbarriers, issued sequence numbers
+    off += round_up(vr::MAX_STAGES * (8 + 8 + 4) + 9 * 4, 128);          // full[] / empty[] mbarriers, issued sequence numbers, job queue
     p.off_tw = off;  off += (7 * 32 + 7 * 4) * 16 + vr::NFFT * 4;        // pass-1 / pass-2 twiddles, Hann window
     p.zpark = park ? 1 : 0;
     p.off_z = off;   off += round_up((park ? 1 : vr::NG) * p.zcap * 8, 128);   // the job's complex baseband samples (per bone group if !park)
@@ -276,7 +277,7 @@ KernelFn pick_kernel(bool fma, int vm, int m, bool ups, bool park) {
     return generic;
 }
 
-struct DeviceInfo { int sm_count = 0; bool attr_set = false; };
+struct DeviceInfo { int sm_count = 0; bool attr_set = false; int* tickets = nullptr; unsigned next_slot = 0; };
 std::mutex g_mu;
 DeviceInfo g_dev[64];
 
@@ -293,10 +294,18 @@ int device_setup(int& dev, int& sm_count) {
         d.sm_count = prop.multiProcessorCount;
         for (int i = 0; i < kNumVariants; ++i)
             CUDA_TRY(cudaFuncSetAttribute(kVariants[i].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        CUDA_TRY(cudaGetSymbolAddress((void**)&d.tickets, vr::g_ticket_pool));
         d.attr_set = true;
     }
     sm_count = d.sm_count;
     return VR_OK;
+}
+
+// a counter pair for one launch with more jobs than CTAs (dynamic job scheduling)
+int* next_ticket_slot(int dev) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    DeviceInfo& d = g_dev[dev];
+    return d.tickets + 2 * (d.next_slot++ % vr::TICKET_SLOTS);
 }
 
 // Plans depend only on shapes and the bone list; the last one is kept per host thread so that a
@@ -349,6 +358,7 @@ int launch(const float* x, int64_t N, int64_t T, int V, int M, const int32_t* sr
     rc = cached_plan(N, T, V, M, src, dst, E, n_fft, hop, img, coef != nullptr, sm_count, ((uintptr_t)x & 15) == 0, p, grid, cps);
     if (rc) return rc;
     p.x = x; p.out = out; p.iq = iq; p.tl = g_timeline;
+    p.ticket = (g_dynamic && !coef && p.n_jobs > grid) ? next_ticket_slot(dev) : nullptr;
     p.coef = coef; p.ups_T = ups_T; p.ups_K = ups_K;
     p.ups_ratio = coef ? (double)(ups_T - 1) / (double)((long long)ups_K * ups_T - 1) : 0.0;
     p.lam_ptr = lam_dev; p.loc_ptr = loc_dev;
