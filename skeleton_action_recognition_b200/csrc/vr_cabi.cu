@@ -198,7 +198,7 @@ int make_plan_z(int64_t N, int64_t T, int V, int M, const int32_t* src, const in
     p.scr_bytes = round_up(std::max(vr::XCH_BYTES, p.eg_max * 128 * NB), 128);
     p.xg_bytes = round_up(2 * vr::NG * 32 * NB * 4, 128);        // double-buffered
     int off = 0;
-    off += round_up(vr::MAX_STAGES * (8 + 8 + 4) + 9 * 4, 128);          // full[] / empty[] mbarriers, issued sequence numbers, job queue
+    off += round_up(vr::MAX_STAGES * (8 + 8 + 4) + 10 * 4, 128);          // full[] / empty[] mbarriers, issued sequence numbers, job queue
     p.off_tw = off;  off += (7 * 32 + 7 * 4) * 16 + vr::NFFT * 4;        // pass-1 / pass-2 twiddles, Hann window
     p.zpark = park ? 1 : 0;
     p.off_z = off;   off += round_up((park ? 1 : vr::NG) * p.zcap * 8, 128);   // the job's complex baseband samples (per bone group if !park)
@@ -358,7 +358,7 @@ int launch(const float* x, int64_t N, int64_t T, int V, int M, const int32_t* sr
     rc = cached_plan(N, T, V, M, src, dst, E, n_fft, hop, img, coef != nullptr, sm_count, ((uintptr_t)x & 15) == 0, p, grid, cps);
     if (rc) return rc;
     p.x = x; p.out = out; p.iq = iq; p.tl = g_timeline;
-    p.ticket = (g_dynamic && !coef && p.n_jobs > grid) ? next_ticket_slot(dev) : nullptr;
+    p.ticket = (g_dynamic && p.n_jobs > grid) ? next_ticket_slot(dev) : nullptr;
     p.coef = coef; p.ups_T = ups_T; p.ups_K = ups_K;
     p.ups_ratio = coef ? (double)(ups_T - 1) / (double)((long long)ups_K * ups_T - 1) : 0.0;
     p.lam_ptr = lam_dev; p.loc_ptr = loc_dev;
