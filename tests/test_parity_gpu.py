@@ -225,3 +225,30 @@ def test_cuda_graph_capture_and_replay():
         torch.cuda.synchronize()
         assert torch.equal(static_y, layer(xb))
         assert torch.equal(static_img, layer.forward_image(xb, 64))
+
+
+def test_dynamic_job_scheduling_concurrent_streams():
+    """Batches with more jobs than CTAs draw their jobs from global ticket counters (one pair per launch, handed out
+    round-robin).  Launches that overlap on two streams must not disturb each other, results must not depend on which
+    CTA took which job, and the counters must re-arm themselves (many launches in a row)."""
+    layer = _layer(wavelength=5e-4)
+    xa = fx.s1_iid(64, seed=21).repeat(24, 1, 1, 1, 1).cuda()        # 1536 sequences > 296 CTAs
+    xb = fx.s1_iid(64, seed=22).repeat(20, 1, 1, 1, 1).cuda()        # 1280
+    xl = fx.s1_iid(2, seed=23, shape=(3, 9000, 25, 2)).cuda()        # long sequences: several jobs each, parked sums
+    want_a, want_b, want_l = layer(xa[:64]).repeat(24, 1, 1), layer(xb[:64]).repeat(20, 1, 1), layer(xl)
+    assert torch.equal(layer(xl[:1]), want_l[:1])
+    sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    outs = []
+    for _ in range(12):
+        with torch.cuda.stream(sa):
+            ya = layer(xa)
+            yl = layer(xl)
+        with torch.cuda.stream(sb):
+            yb = layer(xb)
+            yi = layer.forward_image(xb, 64)
+        outs.append((ya, yb, yl, yi))
+    torch.cuda.synchronize()
+    want_i = torch.nn.functional.interpolate(want_b.unsqueeze(1), 64)
+    for ya, yb, yl, yi in outs:
+        assert torch.equal(ya, want_a) and torch.equal(yb, want_b) and torch.equal(yl, want_l) and torch.equal(yi, want_i)
