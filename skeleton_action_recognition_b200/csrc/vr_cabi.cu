@@ -34,10 +34,11 @@ int fail(int code, const char* fmt, ...) {
     } while (0)
 
 struct Tuning { int warps = 0, ctas_per_sm = 0, stages = 0; };
-Tuning g_tuning;
-unsigned long long* g_timeline = nullptr;
-const bool g_dynamic = getenv("VR_B200_STATIC_JOBS") == nullptr;   // dynamic job scheduling for batches larger than the grid (A/B switch)
-const bool g_pdl = getenv("VR_B200_NO_PDL") == nullptr;   // programmatic dependent launch (A/B switch for profiling)   // profiling only (vr_set_timeline_buffer)
+Tuning g_tuning;                                  // vr_set_tuning (benchmark knob)
+unsigned long long* g_timeline = nullptr;         // vr_set_timeline_buffer (profiling aid)
+// A/B switches for measurements; both features are on unless the variable is set
+const bool g_dynamic = getenv("VR_B200_STATIC_JOBS") == nullptr;   // dynamic job scheduling for batches larger than the grid
+const bool g_pdl = getenv("VR_B200_NO_PDL") == nullptr;            // programmatic dependent launch
 
 // ---- bone partition -----------------------------------------------------------------------------
 // Bones are grouped by source joint (the range phase of a joint is shared by all bones that start
