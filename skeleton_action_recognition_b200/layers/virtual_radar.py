@@ -133,11 +133,21 @@ class VirtualRadar(torch.nn.Module):
 
     def _load_from_state_dict(self, *args, **kwargs):
         super()._load_from_state_dict(*args, **kwargs)
+        self._stft_verified = False      # a checkpoint may carry trained STFT kernels: re-check before the next launch
+
+    def _check_stft(self):
+        """The CUDA path evaluates the analytic Hann-windowed DFT.  A checkpoint whose `stft.wsin/wcos` were trained
+        (reference `train_stft_kernel=True`) would silently be ignored, so the parameters are compared with the
+        analytic kernels once after construction / every `load_state_dict` (one small device-to-host copy)."""
+        if not getattr(self, "_stft_verified", False):
+            self.stft.assert_dft()
+            self._stft_verified = True
 
     def output_shape(self, x_shape):
         return (x_shape[0], self.n_fft, x_shape[2] // self.hop_length + 1)
 
     def _check_input(self, x):
+        self._check_stft()
         if not isinstance(x, torch.Tensor) or x.dim() != 5 or x.shape[1] != 3:
             raise ValueError("expected x of shape (batch, 3, timesteps, vertices, num_graphs), got %s"
                              % (tuple(x.shape) if isinstance(x, torch.Tensor) else type(x),))

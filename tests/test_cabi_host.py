@@ -143,3 +143,12 @@ def test_module_surface_matches_reference():
     layer2 = VirtualRadar(wavelength=1e-3, device="cpu")
     layer2.load_state_dict(sd)
     assert float(layer2.wavelength) == float(layer.wavelength)
+    # ... but a checkpoint with TRAINED STFT kernels must not be silently replaced by the analytic DFT
+    bad = {k: v.clone() for k, v in sd.items()}
+    bad["stft.wsin"][3, 0, 5] += 0.25
+    layer2.load_state_dict(bad)
+    with pytest.raises(NotImplementedError, match="differ from the Hann-windowed Fourier kernels"):
+        layer2(torch.zeros(1, 3, 300, 25, 2))
+    layer2.load_state_dict(sd)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        layer2(torch.zeros(1, 3, 300, 25, 2))
