@@ -131,6 +131,13 @@ int vr_backward_f32(const float* x_dev, const float* iq_dev, const float* grad_o
                     int32_t n_fft, int32_t hop, uint32_t flags,
                     float* gz_work_dev, double* grad_params_dev,
                     float* grad_x_dev /* (N,3,T,V,M) dL/dx, overwritten; NULL = not wanted */, void* stream);
+/* Only the second stage: the caller supplies dL/d(iq) (grad_iq_dev, (N,T,2)) -- used when the STFT is a general,
+ * trainable (n_fft x n_fft) kernel pair evaluated and differentiated outside this library (train_stft_kernel=True,
+ * reference layers/virtual_radar.py:42,75).                                                                       */
+int vr_synth_adjoint_f32(const float* x_dev, const float* grad_iq_dev, int64_t N, int64_t T, int32_t V, int32_t M,
+                         const int32_t* src_host, const int32_t* dst_host, int32_t E,
+                         const float* wavelength_dev, const float* radar_loc_dev, uint32_t flags,
+                         double* grad_params_dev, float* grad_x_dev, void* stream);
 /* the same without dL/dx */
 int vr_backward_params_f32(const float* x_dev, const float* iq_dev, const float* grad_out_dev,
                            int64_t N, int64_t T, int32_t V, int32_t M,

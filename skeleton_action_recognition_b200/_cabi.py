@@ -15,7 +15,7 @@ ABI_VERSION = 1
 SYMBOLS = ("vr_abi_version", "vr_last_error", "vr_forward_f32", "vr_forward_debug_f32",
            "vr_forward_host_f32", "vr_release_host_staging", "vr_plan", "vr_partition_edges",
            "vr_set_tuning", "vr_selftest_rounding", "vr_set_timeline_buffer", "vr_pad_frames_f32",
-           "vr_forward_image_f32", "vr_plan_image", "vr_forward_upsampled_f32", "vr_upsampled_workspace_bytes", "vr_backward_params_f32", "vr_backward_f32")
+           "vr_forward_image_f32", "vr_plan_image", "vr_forward_upsampled_f32", "vr_upsampled_workspace_bytes", "vr_backward_params_f32", "vr_backward_f32", "vr_synth_adjoint_f32")
 
 _lib = None
 
@@ -49,6 +49,8 @@ def lib():
     L.vr_backward_params_f32.restype = ctypes.c_int
     L.vr_backward_f32.argtypes = [vp, vp, vp, i64, i64, i32, i32, c_i32p, c_i32p, i32, vp, vp, i32, i32, u32, vp, vp, vp, vp]
     L.vr_backward_f32.restype = ctypes.c_int
+    L.vr_synth_adjoint_f32.argtypes = [vp, vp, i64, i64, i32, i32, c_i32p, c_i32p, i32, vp, vp, u32, vp, vp, vp]
+    L.vr_synth_adjoint_f32.restype = ctypes.c_int
     L.vr_plan_image.argtypes = [i64, i64, i32, i32, c_i32p, c_i32p, i32, i32, i32, i32, i32, ctypes.POINTER(i64)]
     L.vr_forward_host_f32.argtypes = common + [f32, ctypes.POINTER(f32), i32, i32, u32, vp, i64]
     L.vr_plan.argtypes = [i64, i64, i32, i32, c_i32p, c_i32p, i32, i32, i32, i32, ctypes.POINTER(i64)]

@@ -597,18 +597,29 @@ int vr_backward_params_f32(const float* x_dev, const float* iq_dev, const float*
                            n_fft, hop, flags, gz_work_dev, grad_params_dev, nullptr, stream);
 }
 
+int vr_synth_adjoint_f32(const float* x_dev, const float* grad_iq_dev, int64_t N, int64_t T, int32_t V, int32_t M,
+                         const int32_t* src_host, const int32_t* dst_host, int32_t E,
+                         const float* wavelength_dev, const float* radar_loc_dev, uint32_t flags,
+                         double* grad_params_dev, float* grad_x_dev, void* stream) {
+    // vr_backward_f32 without its first stage: dL/d(iq) comes from the caller (a general STFT differentiated by autograd)
+    return vr_backward_f32(x_dev, nullptr, nullptr, N, T, V, M, src_host, dst_host, E, wavelength_dev, radar_loc_dev,
+                           vr::NFFT, 16, flags | 0x80000000u, const_cast<float*>(grad_iq_dev), grad_params_dev, grad_x_dev, stream);
+}
+
 int vr_backward_f32(const float* x_dev, const float* iq_dev, const float* grad_out_dev,
                     int64_t N, int64_t T, int32_t V, int32_t M,
                     const int32_t* src_host, const int32_t* dst_host, int32_t E,
                     const float* wavelength_dev, const float* radar_loc_dev,
                     int32_t n_fft, int32_t hop, uint32_t flags,
                     float* gz_work_dev, double* grad_params_dev, float* grad_x_dev, void* stream) {
-    if (!x_dev || !iq_dev || !grad_out_dev || !gz_work_dev || !grad_params_dev || !wavelength_dev || !radar_loc_dev)
+    const bool synth_only = (flags & 0x80000000u) != 0;       // internal: gz_work_dev already holds dL/d(iq)
+    flags &= ~0x80000000u;
+    if (!x_dev || !gz_work_dev || !grad_params_dev || !wavelength_dev || !radar_loc_dev || (!synth_only && (!iq_dev || !grad_out_dev)))
         return fail(VR_ERR_ARG, "device pointers must not be null");
     if (flags & ~VR_FLAG_RANGE_FMA) return fail(VR_ERR_ARG, "unknown flags 0x%x", flags);
     if (N <= 0 || T <= 0 || V <= 0 || M <= 0 || hop <= 0) return fail(VR_ERR_SHAPE, "N, T, V, M, hop must be positive");
     if (n_fft != vr::NFFT) return fail(VR_ERR_UNSUPPORTED, "this ABI version implements n_fft=256 only (got %d)", n_fft);
-    if (T <= n_fft / 2) return fail(VR_ERR_SHAPE, "T=%lld must exceed n_fft/2=%d", (long long)T, n_fft / 2);
+    if (!synth_only && T <= n_fft / 2) return fail(VR_ERR_SHAPE, "T=%lld must exceed n_fft/2=%d", (long long)T, n_fft / 2);
     if (T > (1ll << 30)) return fail(VR_ERR_UNSUPPORTED, "T=%lld too long", (long long)T);
     if (!src_host || !dst_host) return fail(VR_ERR_ARG, "edge arrays must not be null");
     if (E <= 0 || E > vr::NG * vr::MAX_EG) return fail(VR_ERR_UNSUPPORTED, "E=%d outside [1, %d]", E, vr::NG * vr::MAX_EG);
@@ -630,12 +641,14 @@ int vr_backward_f32(const float* x_dev, const float* iq_dev, const float* grad_o
     p.fma_range = (flags & VR_FLAG_RANGE_FMA) ? 1 : 0;
     p.inv_E = 1.0f / (float)E;
     cudaStream_t st = (cudaStream_t)stream;
-    CUDA_TRY(cudaMemsetAsync(gz_work_dev, 0, (size_t)N * T * 2 * sizeof(float), st));
     if (grad_x_dev) CUDA_TRY(cudaMemsetAsync(grad_x_dev, 0, (size_t)N * 3 * T * V * M * sizeof(float), st));
-    const long long frames = N * (long long)p.F;
-    const int grid1 = (int)std::min<long long>((frames + vr::BWD_WARPS - 1) / vr::BWD_WARPS, (long long)sm_count * 8);
-    vr::vr_stft_adjoint_kernel<<<grid1, vr::BWD_WARPS * 32, 0, st>>>(p);
-    CUDA_TRY(cudaGetLastError());
+    if (!synth_only) {
+        CUDA_TRY(cudaMemsetAsync(gz_work_dev, 0, (size_t)N * T * 2 * sizeof(float), st));
+        const long long frames = N * (long long)p.F;
+        const int grid1 = (int)std::min<long long>((frames + vr::BWD_WARPS - 1) / vr::BWD_WARPS, (long long)sm_count * 8);
+        vr::vr_stft_adjoint_kernel<<<grid1, vr::BWD_WARPS * 32, 0, st>>>(p);
+        CUDA_TRY(cudaGetLastError());
+    }
     const long long steps = N * T;
     const int grid2 = (int)std::min<long long>((steps + 127) / 128, (long long)sm_count * 16);
     vr::vr_synth_adjoint_kernel<<<grid2, 128, 0, st>>>(p);

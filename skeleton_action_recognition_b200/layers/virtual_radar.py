@@ -54,12 +54,30 @@ class _STFTKernels(torch.nn.Module):
         wcos = (window * np.cos(ang)).astype(np.float32)[:, None, :]
         return torch.from_numpy(wsin), torch.from_numpy(wcos)
 
-    def assert_dft(self):
+    def is_dft(self):
         wsin, wcos = self.analytic(self.n_fft)
-        if not (torch.allclose(self.wsin.detach().cpu(), wsin, atol=1e-6)
-                and torch.allclose(self.wcos.detach().cpu(), wcos, atol=1e-6)):
-            raise NotImplementedError("stft.wsin/wcos differ from the Hann-windowed Fourier kernels; "
-                                      "trained STFT kernels are not supported by the CUDA path")
+        return bool(torch.allclose(self.wsin.detach().cpu(), wsin, atol=1e-6)
+                    and torch.allclose(self.wcos.detach().cpu(), wcos, atol=1e-6))
+
+    def assert_dft(self):
+        if not self.is_dft():
+            raise NotImplementedError("stft.wsin/wcos differ from the Hann-windowed Fourier kernels")
+
+    def logmag(self, iq):
+        """General-kernel path (trained or trainable `wsin`/`wcos`): what the reference computes at
+        layers/virtual_radar.py:124-133 with nnAudio's conv1d STFT, as one float32 GEMM per kernel on the
+        reflect-padded, framed baseband signal (cuBLAS through torch.matmul; differentiable with respect to
+        `wsin`, `wcos` and `iq`).  iq (N,T,2) -> (N, n_fft, T//hop+1)."""
+        n = self.n_fft
+        zp = torch.nn.functional.pad(iq.permute(0, 2, 1), (n // 2, n // 2), mode="reflect")       # (N,2,T+n)
+        frames = zp.unfold(2, n, self.stride)                                                       # (N,2,F,n)
+        wc, ws = self.wcos[:, 0, :].t(), self.wsin[:, 0, :].t()                                     # (n, n_fft)
+        c, s_ = torch.matmul(frames, wc), torch.matmul(frames, ws)                                  # (N,2,F,n_fft)
+        real = c[:, 0] + s_[:, 1]            # stft(I).real - stft(Q).imag, nnAudio's imag = -conv(x, wsin)
+        imag = c[:, 1] - s_[:, 0]            # stft(I).imag + stft(Q).real
+        mag = torch.sqrt(real * real + imag * imag)
+        out = torch.log(mag + 1e-6).transpose(1, 2)                                                 # (N,n_fft,F)
+        return torch.roll(out, n // 2, dims=1)
 
 
 class _RadarFunction(torch.autograd.Function):
@@ -96,6 +114,37 @@ class _RadarFunction(torch.autograd.Function):
         return g_lam, g_loc, gx, None, None
 
 
+class _SynthFunction(torch.autograd.Function):
+    """Complex baseband synthesis only (layers/virtual_radar.py:93-123) -> iq (N,T,2), with gradients for
+    `wavelength`, `radar_location` and `x` (C ABI vr_synth_adjoint_f32).  Used when the STFT is a general,
+    trainable kernel pair and therefore runs outside the fused kernel."""
+
+    @staticmethod
+    def forward(ctx, lam, loc, xc, layer, flags):
+        _, iq = layer._launch(xc, flags, want_iq=True)
+        ctx.save_for_backward(lam, loc, xc)
+        ctx.layer, ctx.flags = layer, flags
+        return iq
+
+    @staticmethod
+    def backward(ctx, grad_iq):
+        lam, loc, xc = ctx.saved_tensors
+        layer = ctx.layer
+        N, _, T, V, M = xc.shape
+        g = grad_iq.contiguous().to(torch.float32)
+        gp = torch.zeros(4, dtype=torch.float64, device=xc.device)
+        gx = torch.empty_like(xc) if ctx.needs_input_grad[2] else None
+        with torch.cuda.device(xc.device):
+            stream = torch.cuda.current_stream(xc.device).cuda_stream
+            rc = _cabi.lib().vr_synth_adjoint_f32(xc.data_ptr(), g.data_ptr(), N, T, V, M, layer._src_c, layer._dst_c,
+                                                  len(layer.src), lam.data_ptr(), loc.data_ptr(), ctx.flags, gp.data_ptr(),
+                                                  gx.data_ptr() if gx is not None else None, ctypes.c_void_p(stream))
+        _cabi.check(rc)
+        g_lam = gp[0].to(torch.float32).reshape(lam.shape) if ctx.needs_input_grad[0] else None
+        g_loc = gp[1:4].to(torch.float32).reshape(loc.shape) if ctx.needs_input_grad[1] else None
+        return g_lam, g_loc, gx, None, None
+
+
 class VirtualRadar(torch.nn.Module):
     """Skeleton sequences -> micro-Doppler log-spectrograms on a B200 (see module docstring)."""
 
@@ -103,17 +152,13 @@ class VirtualRadar(torch.nn.Module):
                  train_wavelength=False, train_radar_location=False, train_stft_kernel=False,
                  n_fft=256, hop_length=16, device='cuda:0'):
         super().__init__()
-        if train_stft_kernel:
-            raise NotImplementedError("trainable STFT kernels are not supported: the CUDA path evaluates the Hann-windowed "
-                                      "DFT with an FFT (the reference's training script never enables the flag, "
-                                      "main_spectrogram.py:128-136)")
         _cabi.lib()   # fail at construction time if the extension is missing
         self.wavelength = torch.nn.Parameter(torch.as_tensor(wavelength, dtype=torch.float32),
                                              requires_grad=bool(train_wavelength))
         self.radar_location = torch.nn.Parameter(torch.as_tensor(radar_location, dtype=torch.float32),
                                                  requires_grad=bool(train_radar_location))
         self.src, self.dst = map(list, zip(*edges))
-        self.stft = _STFTKernels(n_fft, hop_length, False, device)
+        self.stft = _STFTKernels(n_fft, hop_length, bool(train_stft_kernel), device)
         self.n_fft = n_fft
         self.hop_length = hop_length
         self._src_c = _cabi.i32_array(self.src)
@@ -136,12 +181,19 @@ class VirtualRadar(torch.nn.Module):
         self._stft_verified = False      # a checkpoint may carry trained STFT kernels: re-check before the next launch
 
     def _check_stft(self):
-        """The CUDA path evaluates the analytic Hann-windowed DFT.  A checkpoint whose `stft.wsin/wcos` were trained
-        (reference `train_stft_kernel=True`) would silently be ignored, so the parameters are compared with the
-        analytic kernels once after construction / every `load_state_dict` (one small device-to-host copy)."""
+        """The fused kernel evaluates the analytic Hann-windowed DFT with an FFT.  A checkpoint whose `stft.wsin/wcos`
+        were trained (reference `train_stft_kernel=True`) must not silently be replaced by it, so the parameters are
+        compared with the analytic kernels once after construction / every `load_state_dict` (one small
+        device-to-host copy); if they differ -- or are trainable -- the layer switches to the general-kernel path:
+        CUDA synthesis, then the STFT as a library GEMM against `wsin`/`wcos` (`_STFTKernels.logmag`)."""
         if not getattr(self, "_stft_verified", False):
-            self.stft.assert_dft()
+            self._stft_is_dft = self.stft.is_dft()
             self._stft_verified = True
+
+    def _general_stft(self):
+        self._check_stft()
+        return (not self._stft_is_dft) or (torch.is_grad_enabled() and
+                                           (self.stft.wsin.requires_grad or self.stft.wcos.requires_grad))
 
     def output_shape(self, x_shape):
         return (x_shape[0], self.n_fft, x_shape[2] // self.hop_length + 1)
@@ -188,6 +240,13 @@ class VirtualRadar(torch.nn.Module):
         if lam.device != x.device or loc.device != x.device:
             raise RuntimeError("module parameters are on %s but x is on %s; call .to(x.device)" % (lam.device, x.device))
         xc, flags = self._prepare(x)
+        if self._general_stft():     # trained / trainable STFT kernels: synthesis on our kernels, STFT as a GEMM
+            if xc.shape[2] <= self.n_fft // 2:
+                raise ValueError("T=%d must exceed n_fft/2=%d: reflect padding needs it" % (xc.shape[2], self.n_fft // 2))
+            if xc.shape[0] == 0:
+                return self._launch(xc, flags)[0]
+            iq = _SynthFunction.apply(lam, loc, xc, self, flags) if self._needs_grad(x) else self._launch(xc, flags, want_iq=True)[1]
+            return self.stft.logmag(iq)
         if self._needs_grad(x) and xc.shape[0] > 0:
             return _RadarFunction.apply(lam, loc, xc, self, flags)
         return self._launch(xc, flags)[0]
@@ -206,7 +265,7 @@ class VirtualRadar(torch.nn.Module):
         image_size = int(image_size)
         if image_size < 1:
             raise ValueError("image_size must be positive, got %d" % image_size)
-        if self._needs_grad(x):     # gradients wanted: differentiable spectrogram, then torch's resize
+        if self._needs_grad(x) or self._general_stft():     # gradients wanted / general STFT kernels: spectrogram, then torch's resize
             return torch.nn.functional.interpolate(self.forward(x).unsqueeze(1), image_size)
         xc, flags = self._prepare(x)
         N, _, T, V, M = xc.shape
@@ -243,7 +302,7 @@ class VirtualRadar(torch.nn.Module):
         if x.requires_grad and torch.is_grad_enabled():
             raise NotImplementedError("the temporal up-sampling has no backward pass: detach x, or differentiate "
                                       "forward() on an already up-sampled batch")
-        if self._needs_grad():      # trainable radar parameters: materialise the up-sampled batch, differentiable layer
+        if self._needs_grad() or self._general_stft():      # trainable parameters / general STFT kernels: materialise the up-sampled batch
             from ..upsample import pad_frames
             up = pad_frames(xc, k, sigma)
             return self.forward_image(up, img) if img else self.forward(up)
@@ -277,6 +336,9 @@ class VirtualRadar(torch.nn.Module):
         self._check_input(x)
         if x.is_cuda:
             raise ValueError("forward_host takes a CPU tensor; use forward() for CUDA tensors")
+        if self._general_stft():
+            raise NotImplementedError("forward_host evaluates the analytic Hann-windowed DFT only; stft.wsin/wcos are "
+                                      "trained or trainable: use forward() on a CUDA tensor")
         xc, flags = self._prepare(x)
         N, _, T, V, M = xc.shape
         if out is None:

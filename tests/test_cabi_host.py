@@ -130,11 +130,14 @@ def test_module_surface_matches_reference():
         layer(torch.zeros(1, 3, 300, 25, 2))
     with pytest.raises(ValueError):
         layer(torch.zeros(1, 2, 300, 25, 2))
-    with pytest.raises(NotImplementedError):
-        VirtualRadar(train_stft_kernel=True, device="cpu")
-    trainable = VirtualRadar(train_wavelength=True, train_radar_location=True, device="cpu")   # reference flags, :40-41
+    trainable = VirtualRadar(train_wavelength=True, train_radar_location=True, device="cpu")   # reference flags, :40-42
     assert trainable.wavelength.requires_grad and trainable.radar_location.requires_grad
-    assert not trainable.stft.wsin.requires_grad
+    assert not trainable.stft.wsin.requires_grad and not trainable._general_stft()
+    tk = VirtualRadar(train_stft_kernel=True, device="cpu")
+    assert tk.stft.wsin.requires_grad and tk.stft.wcos.requires_grad and not tk.wavelength.requires_grad
+    assert tk._general_stft()                      # trainable kernels: synthesis kernel + GEMM STFT
+    with torch.no_grad():
+        assert not tk._general_stft()              # analytic kernels, no gradient wanted: the fused FFT path
     import copy, pickle
     c = copy.deepcopy(layer)
     assert c.src == layer.src
@@ -147,8 +150,18 @@ def test_module_surface_matches_reference():
     bad = {k: v.clone() for k, v in sd.items()}
     bad["stft.wsin"][3, 0, 5] += 0.25
     layer2.load_state_dict(bad)
-    with pytest.raises(NotImplementedError, match="differ from the Hann-windowed Fourier kernels"):
-        layer2(torch.zeros(1, 3, 300, 25, 2))
+    assert layer2._general_stft()                  # -> CUDA synthesis + GEMM against the loaded kernels
+    with pytest.raises(NotImplementedError, match="analytic Hann-windowed DFT only"):
+        layer2.forward_host(torch.zeros(1, 3, 300, 25, 2))
     layer2.load_state_dict(sd)
+    assert not layer2._general_stft()
     with pytest.raises(RuntimeError, match="no CPU path"):
         layer2(torch.zeros(1, 3, 300, 25, 2))
+    # the GEMM form of the STFT equals the oracle's nnAudio restatement (CPU, float32)
+    from oracle import virtual_radar_oracle as vro
+    from oracle.nnaudio_stft import STFT
+    g = torch.Generator().manual_seed(4)
+    iq = torch.randn(3, 400, 2, generator=g)
+    ref = vro.stft_logmag(iq, STFT(n_fft=256, freq_bins=256, hop_length=16, device="cpu"), 256)
+    got = layer2.stft.logmag(iq)
+    assert got.shape == ref.shape and torch.allclose(got, ref, atol=2e-4, rtol=0)
