@@ -192,8 +192,8 @@ class VirtualRadar(torch.nn.Module):
 
     def _general_stft(self):
         self._check_stft()
-        return (not self._stft_is_dft) or (torch.is_grad_enabled() and
-                                           (self.stft.wsin.requires_grad or self.stft.wcos.requires_grad))
+        return (not self._stft_is_dft) or self.n_fft != self._FUSED_N_FFT or (
+            torch.is_grad_enabled() and (self.stft.wsin.requires_grad or self.stft.wcos.requires_grad))
 
     def output_shape(self, x_shape):
         return (x_shape[0], self.n_fft, x_shape[2] // self.hop_length + 1)
@@ -212,9 +212,12 @@ class VirtualRadar(torch.nn.Module):
         flags = _cabi.VR_FLAG_RANGE_FMA if x.stride(1) == 1 and x.shape[1] > 1 else 0
         return x.contiguous(), flags
 
+    _FUSED_N_FFT = 256      # the fused kernel's FFT size; other n_fft values go through the general-kernel path
+
     def _launch(self, xc, flags, want_iq=False):
         N, _, T, V, M = xc.shape
-        out = torch.empty(self.output_shape(xc.shape), dtype=torch.float32, device=xc.device)
+        n_fft = self._FUSED_N_FFT if want_iq else self.n_fft       # iq does not depend on the STFT parameters
+        out = torch.empty((N, n_fft, T // self.hop_length + 1), dtype=torch.float32, device=xc.device)
         iq = torch.empty((N, T, 2), dtype=torch.float32, device=xc.device) if want_iq else None
         if N == 0:
             return out, iq
@@ -222,7 +225,7 @@ class VirtualRadar(torch.nn.Module):
         with torch.cuda.device(xc.device):
             stream = ctypes.c_void_p(torch.cuda.current_stream(xc.device).cuda_stream)
             args = (xc.data_ptr(), N, T, V, M, self._src_c, self._dst_c, len(self.src), self.wavelength.data_ptr(),
-                    self.radar_location.data_ptr(), self.n_fft, self.hop_length, flags, out.data_ptr())
+                    self.radar_location.data_ptr(), n_fft, self.hop_length, flags, out.data_ptr())
             rc = L.vr_forward_debug_f32(*args, iq.data_ptr(), stream) if want_iq else L.vr_forward_f32(*args, stream)
         _cabi.check(rc)
         return out, iq
@@ -241,8 +244,9 @@ class VirtualRadar(torch.nn.Module):
             raise RuntimeError("module parameters are on %s but x is on %s; call .to(x.device)" % (lam.device, x.device))
         xc, flags = self._prepare(x)
         if self._general_stft():     # trained / trainable STFT kernels: synthesis on our kernels, STFT as a GEMM
-            if xc.shape[2] <= self.n_fft // 2:
-                raise ValueError("T=%d must exceed n_fft/2=%d: reflect padding needs it" % (xc.shape[2], self.n_fft // 2))
+            if xc.shape[2] <= max(self.n_fft, self._FUSED_N_FFT) // 2:
+                raise ValueError("T=%d must exceed n_fft/2=%d: reflect padding needs it"
+                                 % (xc.shape[2], max(self.n_fft, self._FUSED_N_FFT) // 2))
             if xc.shape[0] == 0:
                 return self._launch(xc, flags)[0]
             iq = _SynthFunction.apply(lam, loc, xc, self, flags) if self._needs_grad(x) else self._launch(xc, flags, want_iq=True)[1]

@@ -252,3 +252,16 @@ def test_dynamic_job_scheduling_concurrent_streams():
     want_i = torch.nn.functional.interpolate(want_b.unsqueeze(1), 64)
     for ya, yb, yl, yi in outs:
         assert torch.equal(ya, want_a) and torch.equal(yb, want_b) and torch.equal(yl, want_l) and torch.equal(yi, want_i)
+
+
+@pytest.mark.parametrize("n_fft,hop", [(128, 16), (512, 32), (64, 8)])
+def test_other_n_fft_through_the_general_path(n_fft, hop):
+    """The fused kernel's FFT is 256 points (the reference default, layers/virtual_radar.py:43, and the only value its
+    callers use); other sizes take the synthesis kernel + GEMM STFT path and still match the oracle."""
+    x = fx.s1_iid(3, seed=n_fft, shape=(3, 600, 25, 2))
+    layer = _layer(wavelength=1e-3, n_fft=n_fft, hop_length=hop)
+    out = layer(x.cuda()).cpu().numpy()
+    ref = vro.forward(x, wavelength=1e-3, n_fft=n_fft, hop_length=hop, distance="seq").numpy()
+    assert out.shape == ref.shape == (3, n_fft, 600 // hop + 1)
+    assert vro.parity_ok(vro.parity_report(out, ref))
+    assert tuple(layer.state_dict()["stft.wsin"].shape) == (n_fft, 1, n_fft)
