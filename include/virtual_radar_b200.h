@@ -44,6 +44,14 @@ extern "C" {
                                    sqrt(fma(c,c,fma(b,b,a*a))) instead of sqrt((a*a+b*b)+c*c).
                                    Replaces torch.norm(dim=1) at layers/virtual_radar.py:99.      */
 
+#define VR_FLAG_INPUTS_READY 2u  /* Caller's guarantee for streams of INDEPENDENT batches: the kernel launched just
+                                   before this one on `stream` does not write anything this call reads (x, the two
+                                   parameters) and does not touch `out`.  The launches are programmatic dependent
+                                   launches; with the flag this batch's reads no longer wait for the previous kernel
+                                   to finish, so it starts in the SM slots that kernel has already vacated (its writes
+                                   still wait).  Without the flag (the default, and what the torch module passes)
+                                   plain stream order holds.                                                       */
+
 int         vr_abi_version(void);
 const char* vr_last_error(void);
 

@@ -9,6 +9,7 @@ LIB_PATH = os.environ.get("VR_B200_LIB_OVERRIDE") or os.path.join(_HERE, "lib", 
 
 VR_OK, VR_ERR_ARG, VR_ERR_SHAPE, VR_ERR_UNSUPPORTED, VR_ERR_CUDA = 0, -1, -2, -3, -4
 VR_FLAG_RANGE_FMA = 1
+VR_FLAG_INPUTS_READY = 2
 ABI_VERSION = 1
 
 # every symbol include/virtual_radar_b200.h declares

@@ -350,7 +350,7 @@ int launch(const float* x, int64_t N, int64_t T, int V, int M, const int32_t* sr
     // used for its alignment (the kernel reads the spline coefficients instead)
     if (!x || !out) return fail(VR_ERR_ARG, "x and out must not be null");
     if ((lam_dev == nullptr) != (loc_dev == nullptr)) return fail(VR_ERR_ARG, "wavelength and radar_location must both be device pointers or both be null");
-    if (flags & ~VR_FLAG_RANGE_FMA) return fail(VR_ERR_ARG, "unknown flags 0x%x", flags);
+    if (flags & ~(VR_FLAG_RANGE_FMA | VR_FLAG_INPUTS_READY)) return fail(VR_ERR_ARG, "unknown flags 0x%x", flags);
     int dev, sm_count;
     int rc = device_setup(dev, sm_count);
     if (rc) return rc;
@@ -360,6 +360,7 @@ int launch(const float* x, int64_t N, int64_t T, int V, int M, const int32_t* sr
     if (rc) return rc;
     p.x = x; p.out = out; p.iq = iq; p.tl = g_timeline;
     p.ticket = (g_dynamic && p.n_jobs > grid) ? next_ticket_slot(dev) : nullptr;
+    p.early_reads = (g_pdl && !coef && (flags & VR_FLAG_INPUTS_READY)) ? 1 : 0;   // coef is written by the launch just before
     p.coef = coef; p.ups_T = ups_T; p.ups_K = ups_K;
     p.ups_ratio = coef ? (double)(ups_T - 1) / (double)((long long)ups_K * ups_T - 1) : 0.0;
     p.lam_ptr = lam_dev; p.loc_ptr = loc_dev;

@@ -163,6 +163,10 @@ class VirtualRadar(torch.nn.Module):
         self.hop_length = hop_length
         self._src_c = _cabi.i32_array(self.src)
         self._dst_c = _cabi.i32_array(self.dst)
+        # Opt-in for streams of INDEPENDENT batches (VR_FLAG_INPUTS_READY): set True only if the kernel launched just
+        # before each forward on the same stream neither produces x nor touches the output; consecutive forwards then
+        # overlap (a batch starts in the SM slots the previous one has vacated).  Default: plain stream order.
+        self.assume_inputs_ready = False
 
     # the ctypes arrays are not picklable / deep-copyable (DataParallel.replicate copies __dict__)
     def __getstate__(self):
@@ -217,6 +221,8 @@ class VirtualRadar(torch.nn.Module):
     def _launch(self, xc, flags, want_iq=False):
         N, _, T, V, M = xc.shape
         n_fft = self._FUSED_N_FFT if want_iq else self.n_fft       # iq does not depend on the STFT parameters
+        if getattr(self, "assume_inputs_ready", False):
+            flags |= _cabi.VR_FLAG_INPUTS_READY
         out = torch.empty((N, n_fft, T // self.hop_length + 1), dtype=torch.float32, device=xc.device)
         iq = torch.empty((N, T, 2), dtype=torch.float32, device=xc.device) if want_iq else None
         if N == 0:

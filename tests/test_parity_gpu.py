@@ -265,3 +265,30 @@ def test_other_n_fft_through_the_general_path(n_fft, hop):
     assert out.shape == ref.shape == (3, n_fft, 600 // hop + 1)
     assert vro.parity_ok(vro.parity_report(out, ref))
     assert tuple(layer.state_dict()["stft.wsin"].shape) == (n_fft, 1, n_fft)
+
+
+def test_inputs_ready_flag_overlapping_launches():
+    """VR_FLAG_INPUTS_READY / layer.assume_inputs_ready: back-to-back forwards on independent batches may overlap
+    (reads do not wait for the previous kernel, writes do); the results must be those of plain stream order, for
+    small batches (kernels overlap almost completely), large ones, the image path and long sequences."""
+    layer = _layer(wavelength=5e-4)
+    batches = [fx.s1_iid(n, seed=30 + i).cuda() for i, n in enumerate((40, 256, 7, 700, 128, 1))]
+    long_x = fx.s1_iid(1, seed=40, shape=(3, 6000, 25, 2)).cuda()
+    want = [layer(b) for b in batches]
+    want_img = [layer.forward_image(b, 64) for b in batches]
+    want_long = layer(long_x)
+    torch.cuda.synchronize()
+    layer.assume_inputs_ready = True
+    for _ in range(5):
+        got = [layer(b) for b in batches]
+        got_img = [layer.forward_image(b, 64) for b in batches]
+        got_long = layer(long_x)
+        torch.cuda.synchronize()
+        assert all(torch.equal(a, b) for a, b in zip(got, want))
+        assert all(torch.equal(a, b) for a, b in zip(got_img, want_img))
+        assert torch.equal(got_long, want_long)
+    # the up-sampling path reads coefficients written by its own first launch: the flag must be ignored there
+    from skeleton_action_recognition_b200 import pad_frames
+    xr = fx.s1_iid(6, seed=41, shape=(3, 40, 25, 2)).cuda()
+    assert torch.equal(layer.forward_upsampled(xr, 50, 3), layer(pad_frames(xr, 50, 3)))
+    layer.assume_inputs_ready = False
