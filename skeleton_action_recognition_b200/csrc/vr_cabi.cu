@@ -598,13 +598,24 @@ int vr_backward_params_f32(const float* x_dev, const float* iq_dev, const float*
                            n_fft, hop, flags, gz_work_dev, grad_params_dev, nullptr, stream);
 }
 
+}  // extern "C"
+namespace {
+int backward_impl(const float* x_dev, const float* iq_dev, const float* grad_out_dev,
+                  int64_t N, int64_t T, int32_t V, int32_t M,
+                  const int32_t* src_host, const int32_t* dst_host, int32_t E,
+                  const float* wavelength_dev, const float* radar_loc_dev,
+                  int32_t n_fft, int32_t hop, uint32_t flags, bool synth_only,
+                  float* gz_work_dev, double* grad_params_dev, float* grad_x_dev, void* stream);
+}  // namespace
+extern "C" {
+
 int vr_synth_adjoint_f32(const float* x_dev, const float* grad_iq_dev, int64_t N, int64_t T, int32_t V, int32_t M,
                          const int32_t* src_host, const int32_t* dst_host, int32_t E,
                          const float* wavelength_dev, const float* radar_loc_dev, uint32_t flags,
                          double* grad_params_dev, float* grad_x_dev, void* stream) {
-    // vr_backward_f32 without its first stage: dL/d(iq) comes from the caller (a general STFT differentiated by autograd)
-    return vr_backward_f32(x_dev, nullptr, nullptr, N, T, V, M, src_host, dst_host, E, wavelength_dev, radar_loc_dev,
-                           vr::NFFT, 16, flags | 0x80000000u, const_cast<float*>(grad_iq_dev), grad_params_dev, grad_x_dev, stream);
+    // the second stage of vr_backward_f32 alone: dL/d(iq) comes from the caller (a general STFT differentiated by autograd)
+    return backward_impl(x_dev, nullptr, nullptr, N, T, V, M, src_host, dst_host, E, wavelength_dev, radar_loc_dev,
+                         vr::NFFT, 16, flags, true, const_cast<float*>(grad_iq_dev), grad_params_dev, grad_x_dev, stream);
 }
 
 int vr_backward_f32(const float* x_dev, const float* iq_dev, const float* grad_out_dev,
@@ -613,8 +624,19 @@ int vr_backward_f32(const float* x_dev, const float* iq_dev, const float* grad_o
                     const float* wavelength_dev, const float* radar_loc_dev,
                     int32_t n_fft, int32_t hop, uint32_t flags,
                     float* gz_work_dev, double* grad_params_dev, float* grad_x_dev, void* stream) {
-    const bool synth_only = (flags & 0x80000000u) != 0;       // internal: gz_work_dev already holds dL/d(iq)
-    flags &= ~0x80000000u;
+    return backward_impl(x_dev, iq_dev, grad_out_dev, N, T, V, M, src_host, dst_host, E, wavelength_dev, radar_loc_dev,
+                         n_fft, hop, flags, false, gz_work_dev, grad_params_dev, grad_x_dev, stream);
+}
+
+}  // extern "C"
+namespace {
+int backward_impl(const float* x_dev, const float* iq_dev, const float* grad_out_dev,
+                  int64_t N, int64_t T, int32_t V, int32_t M,
+                  const int32_t* src_host, const int32_t* dst_host, int32_t E,
+                  const float* wavelength_dev, const float* radar_loc_dev,
+                  int32_t n_fft, int32_t hop, uint32_t flags, bool synth_only,
+                  float* gz_work_dev, double* grad_params_dev, float* grad_x_dev, void* stream) {
+    // synth_only: gz_work_dev already holds dL/d(iq); the adjoint STFT is skipped
     if (!x_dev || !gz_work_dev || !grad_params_dev || !wavelength_dev || !radar_loc_dev || (!synth_only && (!iq_dev || !grad_out_dev)))
         return fail(VR_ERR_ARG, "device pointers must not be null");
     if (flags & ~VR_FLAG_RANGE_FMA) return fail(VR_ERR_ARG, "unknown flags 0x%x", flags);
@@ -656,6 +678,8 @@ int vr_backward_f32(const float* x_dev, const float* iq_dev, const float* grad_o
     CUDA_TRY(cudaGetLastError());
     return VR_OK;
 }
+}  // namespace
+extern "C" {
 
 int vr_release_host_staging(void) {
     std::lock_guard<std::mutex> lk(g_stage_mu);
