@@ -221,7 +221,7 @@ class VirtualRadar(torch.nn.Module):
     def _launch(self, xc, flags, want_iq=False):
         N, _, T, V, M = xc.shape
         n_fft = self._FUSED_N_FFT if want_iq else self.n_fft       # iq does not depend on the STFT parameters
-        if getattr(self, "assume_inputs_ready", False):
+        if self.assume_inputs_ready:
             flags |= _cabi.VR_FLAG_INPUTS_READY
         out = torch.empty((N, n_fft, T // self.hop_length + 1), dtype=torch.float32, device=xc.device)
         iq = torch.empty((N, T, 2), dtype=torch.float32, device=xc.device) if want_iq else None
@@ -278,6 +278,8 @@ class VirtualRadar(torch.nn.Module):
         if self._needs_grad(x) or self._general_stft():     # gradients wanted / general STFT kernels: spectrogram, then torch's resize
             return torch.nn.functional.interpolate(self.forward(x).unsqueeze(1), image_size)
         xc, flags = self._prepare(x)
+        if self.assume_inputs_ready:
+            flags |= _cabi.VR_FLAG_INPUTS_READY
         N, _, T, V, M = xc.shape
         out = torch.empty((N, 1, image_size, image_size), dtype=torch.float32, device=x.device)
         if N == 0:
