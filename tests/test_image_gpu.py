@@ -85,3 +85,16 @@ def test_image_errors():
         layer.forward_image(x, 5000)
     with pytest.raises(RuntimeError):
         layer.forward_image(x.cpu(), 256)
+
+
+def test_empty_batch_and_strided_input():
+    layer = _layer(wavelength=5e-4)
+    e = torch.zeros(0, 3, 300, 25, 2, device="cuda")
+    assert tuple(layer(e).shape) == (0, 256, 19)
+    assert tuple(layer.forward_image(e, 64).shape) == (0, 1, 64, 64)
+    assert tuple(layer.forward_upsampled(torch.zeros(0, 3, 40, 25, 2, device="cuda"), 10, 3).shape) == (0, 256, 26)
+    # coordinate axis innermost (notebook-style strides): the image path must pick the same rounding mode as forward
+    g = torch.Generator().manual_seed(77)
+    x = (torch.randn(2, 400, 25, 1, 3, generator=g) * 0.5).permute(0, 4, 1, 2, 3).cuda()
+    assert x.stride(1) == 1
+    assert torch.equal(layer.forward_image(x, 96), torch.nn.functional.interpolate(layer(x).unsqueeze(1), 96))
