@@ -171,6 +171,13 @@ int vr_plan_image(int64_t N, int64_t T, int32_t V, int32_t M,
                   const int32_t* src_host, const int32_t* dst_host, int32_t E,
                   int32_t n_fft, int32_t hop, int32_t image_size, int32_t sm_count, int64_t plan[16]);
 
+/* Host-side view of one job of a launch (test infrastructure for the job split shared by host and device):
+ * geom = [sequence, first output column, columns, first frame, frames spanned, first source sample (chunk aligned),
+ * last source sample, chunks].  image_size = 0 for vr_forward_f32's plan.                                          */
+int vr_job_geometry(int64_t N, int64_t T, int32_t V, int32_t M,
+                    const int32_t* src_host, const int32_t* dst_host, int32_t E,
+                    int32_t n_fft, int32_t hop, int32_t image_size, int64_t job, int64_t geom[8]);
+
 /* Bone -> lane-group assignment used by the synthesis stage (4 groups; all bones sharing a source
  * joint stay in one group so the range phase of that joint is evaluated once).  group_of_edge[E]. */
 int vr_partition_edges(const int32_t* src_host, const int32_t* dst_host, int32_t E, int32_t V,

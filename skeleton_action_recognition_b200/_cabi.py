@@ -16,7 +16,7 @@ ABI_VERSION = 1
 SYMBOLS = ("vr_abi_version", "vr_last_error", "vr_forward_f32", "vr_forward_debug_f32",
            "vr_forward_host_f32", "vr_release_host_staging", "vr_plan", "vr_partition_edges",
            "vr_set_tuning", "vr_selftest_rounding", "vr_set_timeline_buffer", "vr_pad_frames_f32",
-           "vr_forward_image_f32", "vr_plan_image", "vr_forward_upsampled_f32", "vr_upsampled_workspace_bytes", "vr_backward_params_f32", "vr_backward_f32", "vr_synth_adjoint_f32")
+           "vr_forward_image_f32", "vr_plan_image", "vr_forward_upsampled_f32", "vr_upsampled_workspace_bytes", "vr_backward_params_f32", "vr_backward_f32", "vr_synth_adjoint_f32", "vr_job_geometry")
 
 _lib = None
 
@@ -52,6 +52,8 @@ def lib():
     L.vr_backward_f32.restype = ctypes.c_int
     L.vr_synth_adjoint_f32.argtypes = [vp, vp, i64, i64, i32, i32, c_i32p, c_i32p, i32, vp, vp, u32, vp, vp, vp]
     L.vr_synth_adjoint_f32.restype = ctypes.c_int
+    L.vr_job_geometry.argtypes = [i64, i64, i32, i32, c_i32p, c_i32p, i32, i32, i32, i32, i64, ctypes.POINTER(i64)]
+    L.vr_job_geometry.restype = ctypes.c_int
     L.vr_plan_image.argtypes = [i64, i64, i32, i32, c_i32p, c_i32p, i32, i32, i32, i32, i32, ctypes.POINTER(i64)]
     L.vr_forward_host_f32.argtypes = common + [f32, ctypes.POINTER(f32), i32, i32, u32, vp, i64]
     L.vr_plan.argtypes = [i64, i64, i32, i32, c_i32p, c_i32p, i32, i32, i32, i32, ctypes.POINTER(i64)]
@@ -111,6 +113,15 @@ def plan_image(N, T, V, M, src, dst, image_size, n_fft=256, hop=16, sm_count=148
     out = (ctypes.c_int64 * 16)()
     check(lib().vr_plan_image(N, T, V, M, i32_array(src), i32_array(dst), len(src), n_fft, hop, image_size, sm_count, out))
     return dict(zip(IMAGE_PLAN_FIELDS, [int(v) for v in out]))
+
+
+GEOM_FIELDS = ("sequence", "first_column", "columns", "first_frame", "frames", "lo", "hi", "chunks")
+
+
+def job_geometry(N, T, V, M, src, dst, job, image_size=0, n_fft=256, hop=16):
+    out = (ctypes.c_int64 * 8)()
+    check(lib().vr_job_geometry(N, T, V, M, i32_array(src), i32_array(dst), len(src), n_fft, hop, image_size, job, out))
+    return dict(zip(GEOM_FIELDS, [int(v) for v in out]))
 
 
 def selftest_rounding(n, wavelength):

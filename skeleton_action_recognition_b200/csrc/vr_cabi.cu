@@ -434,6 +434,19 @@ int vr_forward_image_f32(const float* x_dev, int64_t N, int64_t T, int32_t V, in
                   n_fft, hop, flags, image_size, out_dev, nullptr, (cudaStream_t)stream);
 }
 
+int vr_job_geometry(int64_t N, int64_t T, int32_t V, int32_t M, const int32_t* src_host, const int32_t* dst_host,
+                    int32_t E, int32_t n_fft, int32_t hop, int32_t image_size, int64_t job, int64_t geom[8]) {
+    if (!geom) return fail(VR_ERR_ARG, "geom must not be null");
+    vr::Params p;
+    int grid, cps;
+    int rc = make_plan(N, T, V, M, src_host, dst_host, E, n_fft, hop, image_size, false, 148, true, p, grid, cps);
+    if (rc) return rc;
+    if (job < 0 || job >= p.n_jobs) return fail(VR_ERR_ARG, "job %lld outside [0, %lld)", (long long)job, (long long)p.n_jobs);
+    const vr::JobGeom g = vr::job_geom((int)job, p.jobs_per_seq, p.FJ, p.ncols, p.img, p.cscale, p.F, hop, (int)T);
+    geom[0] = g.n; geom[1] = g.c0; geom[2] = g.nc; geom[3] = g.f0; geom[4] = g.nf; geom[5] = g.lo; geom[6] = g.hi; geom[7] = g.nchunks;
+    return VR_OK;
+}
+
 int vr_plan_image(int64_t N, int64_t T, int32_t V, int32_t M, const int32_t* src_host, const int32_t* dst_host,
                   int32_t E, int32_t n_fft, int32_t hop, int32_t image_size, int32_t sm_count, int64_t plan[16]) {
     if (!plan) return fail(VR_ERR_ARG, "plan must not be null");

@@ -4,6 +4,7 @@ import ctypes
 import os
 import re
 
+import numpy as np
 import pytest
 
 from tests.conftest import ROOT
@@ -165,3 +166,36 @@ def test_module_surface_matches_reference():
     ref = vro.stft_logmag(iq, STFT(n_fft=256, freq_bins=256, hop_length=16, device="cpu"), 256)
     got = layer2.stft.logmag(iq)
     assert got.shape == ref.shape and torch.allclose(got, ref, atol=2e-4, rtol=0)
+
+
+@pytest.mark.parametrize("T,hop,image", [(300, 16, 0), (300, 16, 256), (129, 16, 0), (5000, 16, 0), (75000, 16, 256),
+                                         (75000, 16, 0), (4095, 16, 256), (4096, 16, 256), (20000, 16, 100), (9000, 16, 300),
+                                         (3000, 16, 64), (700, 8, 256), (1001, 100, 128), (2500, 32, 77), (300, 16, 1),
+                                         (165000, 16, 256), (6400, 16, 37), (333, 7, 19)])
+def test_job_split_covers_every_column_and_fits_the_z_buffer(cabi, T, hop, image):
+    """The job split (shared host/device code: col_frame, job_geom, the planner's column-per-job search): the jobs of a
+    sequence tile its output columns exactly once, every frame a column shows has all of its reflect-padded samples
+    inside the job's [lo, hi], and the span fits the planned z buffer and chunk count."""
+    from oracle import resize
+    from skeleton_action_recognition_b200 import edges
+    src, dst = map(list, zip(*edges))
+    F = T // hop + 1
+    plan = cabi.plan_image(2, T, 25, 2, src, dst, image, hop=hop) if image else cabi.plan(2, T, 25, 2, src, dst, hop=hop)
+    ncols = image if image else F
+    fmap = resize.nearest_index(image, F) if image else np.arange(F)
+    jps = plan["jobs_per_seq"]
+    nxt = 0
+    for j in range(jps):
+        g = cabi.job_geometry(2, T, 25, 2, src, dst, jps + j, image_size=image, hop=hop)      # jobs of the second sequence
+        assert g["sequence"] == 1 and g["first_column"] == nxt and g["columns"] >= 1
+        nxt += g["columns"]
+        cols = np.arange(g["first_column"], g["first_column"] + g["columns"])
+        frames = fmap[cols]
+        assert frames[0] == g["first_frame"] and frames[-1] == g["first_frame"] + g["frames"] - 1
+        s = frames[:, None] * hop - 128 + np.arange(256)[None, :]
+        s = np.abs(s)
+        s = np.where(s >= T, 2 * (T - 1) - s, s)
+        assert s.min() >= g["lo"] and s.max() <= g["hi"] and g["lo"] % 32 == 0 and 0 <= g["lo"] and g["hi"] <= T - 1
+        assert g["hi"] - g["lo"] + 1 <= plan["z_capacity"] and g["chunks"] <= plan["chunks_per_job"]
+        assert g["chunks"] == (g["hi"] - g["lo"]) // 32 + 1
+    assert nxt == ncols
