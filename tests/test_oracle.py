@@ -198,3 +198,14 @@ def test_analytic_gradient_wrt_x_matches_autograd():
     # reference quirk: an all-zero body has rcs = 0 and the graph's sqrt(rcs) (layers/virtual_radar.py:118) has an
     # infinite derivative there, so the reference's autograd returns NaN for that body; the closed form gives 0
     assert np.isnan(gx_a[~present]).all() and np.all(gx_n[~present] == 0)
+
+
+def test_resize_index_random_sizes_vs_torch():
+    """200 random (in, out) pairs, incl. the float32-rounding-sensitive ones (large in, odd out)."""
+    from oracle import resize
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        n_in, n_out = int(rng.integers(1, 12000)), int(rng.integers(1, 1500))
+        x = torch.arange(n_in, dtype=torch.float32).reshape(1, 1, 1, n_in)
+        ref = torch.nn.functional.interpolate(x, (1, n_out)).reshape(-1).numpy().astype(np.int64)
+        assert np.array_equal(resize.nearest_index(n_out, n_in), ref), (n_in, n_out)
