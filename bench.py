@@ -166,7 +166,7 @@ def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     import __graft_entry__ as ge
-    ge.build()
+    ge.build_product()
     from skeleton_action_recognition_b200 import VirtualRadar, _cabi
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"

@@ -171,6 +171,15 @@ int vr_plan_image(int64_t N, int64_t T, int32_t V, int32_t M,
                   const int32_t* src_host, const int32_t* dst_host, int32_t E,
                   int32_t n_fft, int32_t hop, int32_t image_size, int32_t sm_count, int64_t plan[16]);
 
+/* Host-side plan of the team-job schedule (see vr_set_schedule) for vr_forward_f32, callable without a GPU:
+ *   [0] grid  [1] block (8 synthesis warps + one producer warp per team)  [2] dynamic smem bytes  [3] ring stages per
+ *   team  [4] teams per CTA  [5] bytes per stage (max of a chunk's three planes and the output tile, which is built in
+ *   the stage of a job's last chunk)  [6] bytes between the teams' z planes  [7] 1 if the automatic schedule picks it
+ *   for this batch size.  VR_ERR_UNSUPPORTED if the shape does not qualify.                                          */
+int vr_plan_team(int64_t N, int64_t T, int32_t V, int32_t M,
+                 const int32_t* src_host, const int32_t* dst_host, int32_t E,
+                 int32_t n_fft, int32_t hop, int32_t sm_count, int64_t plan[8]);
+
 /* Host-side view of one job of a launch (test infrastructure for the job split shared by host and device):
  * geom = [sequence, first output column, columns, first frame, frames spanned, first source sample (chunk aligned),
  * last source sample, chunks].  image_size = 0 for vr_forward_f32's plan.                                          */
@@ -191,6 +200,13 @@ int vr_selftest_rounding(uint64_t n, float wavelength, uint64_t mismatches[3]);
 /* Benchmark/tuning knob (process-wide, 0 = library default): warps per CTA (<=12), CTAs per SM
  * targeted (<=4), cap on TMA ring stages.  Not needed for normal use.                             */
 int vr_set_tuning(int warps, int ctas_per_sm, int stages);
+
+/* Benchmark knob (process-wide): which of the two schedules of the fused forward kernel a launch takes.  -1 (default)
+ * automatic: batches with at least three sequences per team slot (592 on a B200) run the team-job schedule -- every
+ * team of 4 warps owns a whole sequence, no CTA-wide barriers -- smaller ones the cooperative schedule (both teams of
+ * a CTA share a sequence: half the latency per sequence); 0: always cooperative; 1: team jobs whenever the shape
+ * qualifies (one job per sequence, plain output, TMA-loadable chunks).  The results are bit-identical.             */
+int vr_set_schedule(int mode);
 
 /* Profiling aid (process-wide; NULL = off, the default): when set, every CTA of subsequent launches
  * writes 8 uint64 to dev_buf[8*blockIdx.x ..]: %globaltimer (ns) at [0] entry, [1] prologue done,

@@ -5,7 +5,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("VR_B200_LIB_OVERRIDE") or os.path.join(_HERE, "lib", "libvirtual_radar_b200.so")  # override: build experiments only
+LIB_PATH = os.path.join(_HERE, "lib", "libvirtual_radar_b200.so")
 
 VR_OK, VR_ERR_ARG, VR_ERR_SHAPE, VR_ERR_UNSUPPORTED, VR_ERR_CUDA = 0, -1, -2, -3, -4
 VR_FLAG_RANGE_FMA = 1
@@ -16,7 +16,8 @@ ABI_VERSION = 1
 SYMBOLS = ("vr_abi_version", "vr_last_error", "vr_forward_f32", "vr_forward_debug_f32",
            "vr_forward_host_f32", "vr_release_host_staging", "vr_plan", "vr_partition_edges",
            "vr_set_tuning", "vr_selftest_rounding", "vr_set_timeline_buffer", "vr_pad_frames_f32",
-           "vr_forward_image_f32", "vr_plan_image", "vr_forward_upsampled_f32", "vr_upsampled_workspace_bytes", "vr_backward_params_f32", "vr_backward_f32", "vr_synth_adjoint_f32", "vr_job_geometry")
+           "vr_forward_image_f32", "vr_plan_image", "vr_forward_upsampled_f32", "vr_upsampled_workspace_bytes", "vr_backward_params_f32", "vr_backward_f32", "vr_synth_adjoint_f32", "vr_job_geometry",
+           "vr_set_schedule", "vr_plan_team")
 
 _lib = None
 
@@ -59,6 +60,10 @@ def lib():
     L.vr_plan.argtypes = [i64, i64, i32, i32, c_i32p, c_i32p, i32, i32, i32, i32, ctypes.POINTER(i64)]
     L.vr_partition_edges.argtypes = [c_i32p, c_i32p, i32, i32, c_i32p]
     L.vr_set_tuning.argtypes = [ctypes.c_int] * 3
+    L.vr_plan_team.argtypes = [i64, i64, i32, i32, c_i32p, c_i32p, i32, i32, i32, i32, ctypes.POINTER(i64)]
+    L.vr_plan_team.restype = ctypes.c_int
+    L.vr_set_schedule.argtypes = [ctypes.c_int]
+    L.vr_set_schedule.restype = ctypes.c_int
     L.vr_pad_frames_f32.argtypes = [vp, i64, i64, i32, i32, i32, f32, vp, vp]
     L.vr_pad_frames_f32.restype = ctypes.c_int
     L.vr_set_timeline_buffer.argtypes = [vp]
@@ -113,6 +118,20 @@ def plan_image(N, T, V, M, src, dst, image_size, n_fft=256, hop=16, sm_count=148
     out = (ctypes.c_int64 * 16)()
     check(lib().vr_plan_image(N, T, V, M, i32_array(src), i32_array(dst), len(src), n_fft, hop, image_size, sm_count, out))
     return dict(zip(IMAGE_PLAN_FIELDS, [int(v) for v in out]))
+
+
+TEAM_PLAN_FIELDS = ("grid", "block", "smem_bytes", "ring_stages_per_team", "teams_per_cta", "stage_bytes", "z_stride", "automatic")
+
+
+def plan_team(N, T, V, M, src, dst, n_fft=256, hop=16, sm_count=148):
+    out = (ctypes.c_int64 * 8)()
+    check(lib().vr_plan_team(N, T, V, M, i32_array(src), i32_array(dst), len(src), n_fft, hop, sm_count, out))
+    return dict(zip(TEAM_PLAN_FIELDS, [int(v) for v in out]))
+
+
+def set_schedule(mode):
+    """-1 automatic (default), 0 cooperative kernel only, 1 team-job kernel whenever the shape qualifies."""
+    check(lib().vr_set_schedule(int(mode)))
 
 
 GEOM_FIELDS = ("sequence", "first_column", "columns", "first_frame", "frames", "lo", "hi", "chunks")

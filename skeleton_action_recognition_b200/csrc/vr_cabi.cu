@@ -36,9 +36,19 @@ int fail(int code, const char* fmt, ...) {
 struct Tuning { int warps = 0, ctas_per_sm = 0, stages = 0; };
 Tuning g_tuning;                                  // vr_set_tuning (benchmark knob)
 unsigned long long* g_timeline = nullptr;         // vr_set_timeline_buffer (profiling aid)
-// A/B switches for measurements; both features are on unless the variable is set
-const bool g_dynamic = getenv("VR_B200_STATIC_JOBS") == nullptr;   // dynamic job scheduling for batches larger than the grid
-const bool g_pdl = getenv("VR_B200_NO_PDL") == nullptr;            // programmatic dependent launch
+// A/B builds for measurements are made with compile-time macros (tools/ab.py builds the variants); the shipped library
+// has no environment switches.
+#ifdef VR_AB_STATIC_JOBS
+constexpr bool g_dynamic = false;                 // round-robin jobs instead of the ticket counter
+#else
+constexpr bool g_dynamic = true;                  // dynamic job scheduling for batches larger than the grid
+#endif
+#ifdef VR_AB_NO_PDL
+constexpr bool g_pdl = false;
+#else
+constexpr bool g_pdl = true;                      // programmatic dependent launch
+#endif
+int g_schedule = -1;                              // vr_set_schedule: -1 automatic, 0 cooperative kernel only, 1 team-job kernel whenever it applies
 
 // ---- bone partition -----------------------------------------------------------------------------
 // Bones are grouped by source joint (the range phase of a joint is shared by all bones that start
@@ -253,8 +263,58 @@ int make_plan(int64_t N, int64_t T, int V, int M, const int32_t* src, const int3
     return make_plan_z(N, T, V, M, src, dst, E, n_fft, hop, img, ups, sm_count, x_aligned, caps[0], true, p, grid, ctas_per_sm);
 }
 
-// kernel variants: range rounding mode x compile-time V*M (plane stride as an immediate); VM=0 is generic
+// ---- team-job schedule (vr_team_kernel) -----------------------------------------------------------
+// Applies to batches of short sequences (one job per sequence, plain (N, n_fft, F) output in one bulk store, every
+// chunk loadable by TMA).  Every team of 4 warps owns a whole sequence: private 2-stage ring, single z plane with
+// parked partial sums, output tile built in the stage of the job's last chunk.  `p` comes from make_plan (bone
+// tables, shapes); this re-lays the shared memory.  Returns false when the shape does not qualify.
+bool make_team_plan(vr::Params& p, int sm_count, int& grid) {
+    if (p.jobs_per_seq != 1 || p.img || !p.bulk_out || !p.tma_in) return false;
+    const int T = (int)p.T;
+    const int last = T - (T - 1) / vr::TL * vr::TL;                      // time steps of the last chunk
+    if ((last * p.VM) % 4 != 0) return false;                            // its planes must be 16-byte multiples for TMA
+    const int NB = (p.M % 2 == 0) ? 2 : 1;
+    const int W = vr::TJ_TEAMS * vr::NG;
+    p.W = W;
+    p.zpark = 1;
+    p.team_jobs = 1;
+    p.zcap = round_up(T, 16);
+    p.z_stride = round_up(p.zcap * 8, 128);
+    p.stage_bytes = round_up(std::max(3 * p.plane_floats * 4, vr::NFFT * p.F * 4), 128);
+    p.scr_bytes = round_up(std::max(vr::XCH_BYTES, p.eg_max * 128 * NB), 128);
+    p.xg_bytes = round_up(2 * vr::NG * 32 * NB * 4, 128);
+    int off = 128;                                                       // mbarriers + stage metadata
+    p.off_tw = off;  off += round_up((7 * 32 + 7 * 4) * 16 + vr::NFFT * 4, 128);
+    p.off_z = off;   off += vr::TJ_TEAMS * p.z_stride;
+    p.off_zp = off;  off += vr::TJ_TEAMS * 2 * vr::NG * 32 * 8;
+    p.off_scr = off; off += W * p.scr_bytes;
+    p.off_xg = off;  off += vr::TJ_TEAMS * p.xg_bytes;
+    p.off_ring = off; off += vr::TJ_TEAMS * vr::TJ_RS * p.stage_bytes;
+    p.S = vr::TJ_RS;
+    p.smem_bytes = off;
+    const int SMEM_SM = 233472;
+    if (p.smem_bytes > SMEM_SM / 2 - 1024) return false;                 // two CTAs per SM or not at all
+    grid = (int)std::min<long long>((p.n_jobs + vr::TJ_TEAMS - 1) / vr::TJ_TEAMS, (long long)sm_count * 2);
+    return true;
+}
+
 typedef void (*KernelFn)(const vr::Params);
+struct TeamVariant { bool fma; int vm; int nb; KernelFn fn; };
+#define VR_TEAM_VARIANT(VM, NB) {false, VM, NB, vr::vr_team_kernel<false, VM, NB>}, {true, VM, NB, vr::vr_team_kernel<true, VM, NB>}
+const TeamVariant kTeamVariants[] = { VR_TEAM_VARIANT(0, 1), VR_TEAM_VARIANT(0, 2), VR_TEAM_VARIANT(50, 2) };
+const int kNumTeamVariants = sizeof(kTeamVariants) / sizeof(kTeamVariants[0]);
+KernelFn pick_team_kernel(bool fma, int vm, int m) {
+    const int nb = (m % 2 == 0) ? 2 : 1;
+    KernelFn generic = nullptr;
+    for (int i = 0; i < kNumTeamVariants; ++i) {
+        if (kTeamVariants[i].fma != fma || kTeamVariants[i].nb != nb) continue;
+        if (kTeamVariants[i].vm == vm) return kTeamVariants[i].fn;
+        if (kTeamVariants[i].vm == 0) generic = kTeamVariants[i].fn;
+    }
+    return generic;
+}
+
+// kernel variants: range rounding mode x compile-time V*M (plane stride as an immediate); VM=0 is generic
 struct Variant { bool fma; int vm; int nb; bool ups; bool park; KernelFn fn; };
 #define VR_VARIANT(VM, NB, UPS, PARK) {false, VM, NB, UPS, PARK, vr::vr_fused_kernel<false, VM, NB, UPS, PARK>}, \
                                       {true, VM, NB, UPS, PARK, vr::vr_fused_kernel<true, VM, NB, UPS, PARK>}
@@ -278,6 +338,8 @@ KernelFn pick_kernel(bool fma, int vm, int m, bool ups, bool park) {
     return generic;
 }
 
+constexpr int TEAM_AUTO_WAVES = 3;      // automatic schedule: team-job kernel from this many jobs per team slot
+
 struct DeviceInfo { int sm_count = 0; bool attr_set = false; int* tickets = nullptr; unsigned next_slot = 0; };
 std::mutex g_mu;
 DeviceInfo g_dev[64];
@@ -295,6 +357,8 @@ int device_setup(int& dev, int& sm_count) {
         d.sm_count = prop.multiProcessorCount;
         for (int i = 0; i < kNumVariants; ++i)
             CUDA_TRY(cudaFuncSetAttribute(kVariants[i].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        for (int i = 0; i < kNumTeamVariants; ++i)
+            CUDA_TRY(cudaFuncSetAttribute(kTeamVariants[i].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         CUDA_TRY(cudaGetSymbolAddress((void**)&d.tickets, vr::g_ticket_pool));
         d.attr_set = true;
     }
@@ -358,8 +422,19 @@ int launch(const float* x, int64_t N, int64_t T, int V, int M, const int32_t* sr
     int grid, cps;
     rc = cached_plan(N, T, V, M, src, dst, E, n_fft, hop, img, coef != nullptr, sm_count, ((uintptr_t)x & 15) == 0, p, grid, cps);
     if (rc) return rc;
+    // schedule: batches with several sequences per team slot take the team-job kernel (no CTA-wide barriers, a double
+    // buffer per team); small batches keep the cooperative kernel, whose latency per sequence is half
+    bool team = false;
+    if (!coef && !iq && !g_timeline && g_schedule != 0) {
+        vr::Params q = p;
+        int tg = 0;
+        if (make_team_plan(q, sm_count, tg) && (g_schedule == 1 || q.n_jobs >= (long long)TEAM_AUTO_WAVES * sm_count * 2 * vr::TJ_TEAMS)) {
+            p = q; grid = tg; team = true;
+        }
+    }
+    const int job_slots = team ? grid * vr::TJ_TEAMS : grid;
     p.x = x; p.out = out; p.iq = iq; p.tl = g_timeline;
-    p.ticket = (g_dynamic && p.n_jobs > grid) ? next_ticket_slot(dev) : nullptr;
+    p.ticket = (g_dynamic && p.n_jobs > job_slots) ? next_ticket_slot(dev) : nullptr;
     p.early_reads = (g_pdl && !coef && (flags & VR_FLAG_INPUTS_READY)) ? 1 : 0;   // coef is written by the launch just before
     p.coef = coef; p.ups_T = ups_T; p.ups_K = ups_K;
     p.ups_ratio = coef ? (double)(ups_T - 1) / (double)((long long)ups_K * ups_T - 1) : 0.0;
@@ -370,13 +445,15 @@ int launch(const float* x, int64_t N, int64_t T, int V, int M, const int32_t* sr
     // the tail of the previous kernel in the stream; the kernel executes griddepcontrol.wait before
     // its first global-memory access, so stream order is preserved.
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)(p.W + 1) * 32);
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(team ? (unsigned)vr::TJ_THREADS : (unsigned)(p.W + 1) * 32);
     cfg.dynamicSmemBytes = (size_t)p.smem_bytes; cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, pick_kernel((flags & VR_FLAG_RANGE_FMA) != 0, p.VM, p.M, coef != nullptr, p.zpark != 0), p));
+    KernelFn fn = team ? pick_team_kernel((flags & VR_FLAG_RANGE_FMA) != 0, p.VM, p.M)
+                       : pick_kernel((flags & VR_FLAG_RANGE_FMA) != 0, p.VM, p.M, coef != nullptr, p.zpark != 0);
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, fn, p));
     return VR_OK;
 }
 
@@ -401,6 +478,12 @@ int vr_set_tuning(int warps, int ctas_per_sm, int stages) {
     if (warps < 0 || warps > vr::MAX_WARPS || ctas_per_sm < 0 || ctas_per_sm > 4 || stages < 0)
         return fail(VR_ERR_ARG, "bad tuning (%d,%d,%d)", warps, ctas_per_sm, stages);
     g_tuning.warps = warps; g_tuning.ctas_per_sm = ctas_per_sm; g_tuning.stages = stages;
+    return VR_OK;
+}
+
+int vr_set_schedule(int mode) {
+    if (mode < -1 || mode > 1) return fail(VR_ERR_ARG, "schedule must be -1 (automatic), 0 (cooperative) or 1 (team jobs), got %d", mode);
+    g_schedule = mode;
     return VR_OK;
 }
 
@@ -545,6 +628,7 @@ int pad_launch(const float* x_dev, int64_t N, int64_t T, int32_t V, int32_t M, i
     long long nc = budget / (12ll * T);
     if (nc < 1) return fail(VR_ERR_UNSUPPORTED, "T=%lld too long for the shared-memory spline solve (max %d frames)", (long long)T, 200 * 1024 / 20);
     nc = std::min<long long>(nc, p.VM);
+    nc = std::min<long long>(nc, 1024);                          // one thread per column solves its spline (1024 threads per CTA)
     p.ncb = (int)((p.VM + nc - 1) / nc);
     p.nc = (int)((p.VM + p.ncb - 1) / p.ncb);                    // even out the blocks
     const size_t smem = (size_t)p.T * p.nc * 12 + (size_t)p.T * 8 + 16;
@@ -729,6 +813,22 @@ int vr_plan(int64_t N, int64_t T, int32_t V, int32_t M, const int32_t* src_host,
     plan[0] = grid; plan[1] = (p.W + 1) * 32; plan[2] = p.smem_bytes; plan[3] = p.S; plan[4] = p.FJ;
     plan[5] = p.jobs_per_seq; plan[6] = p.FB; plan[7] = p.tma_in; plan[8] = p.bulk_out; plan[9] = p.cmax;
     plan[10] = p.eg_max; plan[11] = p.sg_max; plan[12] = p.zcap; plan[13] = cps; plan[14] = vr::TL; plan[15] = vr::NG;
+    return VR_OK;
+}
+
+int vr_plan_team(int64_t N, int64_t T, int32_t V, int32_t M, const int32_t* src_host, const int32_t* dst_host,
+                 int32_t E, int32_t n_fft, int32_t hop, int32_t sm_count, int64_t plan[8]) {
+    if (!plan) return fail(VR_ERR_ARG, "plan must not be null");
+    vr::Params p;
+    int grid, cps;
+    const int sms = sm_count > 0 ? sm_count : 148;
+    int rc = make_plan(N, T, V, M, src_host, dst_host, E, n_fft, hop, 0, false, sms, true, p, grid, cps);
+    if (rc) return rc;
+    if (!make_team_plan(p, sms, grid))
+        return fail(VR_ERR_UNSUPPORTED, "the team-job schedule does not apply to this shape (needs one job per sequence, a bulk-stored tile, TMA-loadable chunks and room for two CTAs per SM)");
+    plan[0] = grid; plan[1] = vr::TJ_THREADS; plan[2] = p.smem_bytes; plan[3] = vr::TJ_RS; plan[4] = vr::TJ_TEAMS;
+    plan[5] = p.stage_bytes; plan[6] = p.z_stride;
+    plan[7] = (p.n_jobs >= (long long)TEAM_AUTO_WAVES * sms * 2 * vr::TJ_TEAMS) ? 1 : 0;
     return VR_OK;
 }
 

@@ -180,35 +180,57 @@ class VirtualRadar(torch.nn.Module):
         self._src_c = _cabi.i32_array(self.src)
         self._dst_c = _cabi.i32_array(self.dst)
 
-    def _load_from_state_dict(self, *args, **kwargs):
-        super()._load_from_state_dict(*args, **kwargs)
-        self._stft_verified = False      # a checkpoint may carry trained STFT kernels: re-check before the next launch
-
     def _check_stft(self):
-        """The fused kernel evaluates the analytic Hann-windowed DFT with an FFT.  A checkpoint whose `stft.wsin/wcos`
-        were trained (reference `train_stft_kernel=True`) must not silently be replaced by it, so the parameters are
-        compared with the analytic kernels once after construction / every `load_state_dict` (one small
-        device-to-host copy); if they differ -- or are trainable -- the layer switches to the general-kernel path:
-        CUDA synthesis, then the STFT as a library GEMM against `wsin`/`wcos` (`_STFTKernels.logmag`)."""
-        if not getattr(self, "_stft_verified", False):
+        """The fused kernel evaluates the analytic Hann-windowed DFT with an FFT.  Trained `stft.wsin/wcos` (reference
+        `train_stft_kernel=True`, or a checkpoint of such a model) must never silently be replaced by it, so the
+        parameters are compared with the analytic kernels (one small device-to-host copy) whenever they may have
+        changed: the verdict is cached against the tensors' identity and version counters, which every in-place
+        update through the parameters -- optimizer step, `load_state_dict`, `wsin.copy_()`, `.to()` -- changes.  (Writes
+        through `wsin.data` bypass PyTorch's version counters; call `invalidate_stft_cache()` after such an edit.)"""
+        if getattr(self, "_stft_trusted", False):       # a DataParallel replica: the parent module has just checked
+            return
+        key = tuple((t.data_ptr(), t._version, t.device) for t in (self.stft.wsin, self.stft.wcos))
+        if getattr(self, "_stft_key", None) != key:
             self._stft_is_dft = self.stft.is_dft()
-            self._stft_verified = True
+            self._stft_key = key
+
+    def invalidate_stft_cache(self):
+        self._stft_key = None
+
+    def _replicate_for_data_parallel(self):
+        if not (self.stft.wsin.requires_grad or self.stft.wcos.requires_grad):
+            self._check_stft()                          # once on the parent instead of once per replica and forward
+        replica = super()._replicate_for_data_parallel()
+        replica._stft_trusted = True
+        return replica
 
     def _general_stft(self):
+        """True -> CUDA synthesis, then the STFT against `wsin`/`wcos` as they are (`_STFTKernels.logmag`).  Trainable
+        kernels always take this path, with or without grad mode: an eval pass of a model being trained must see the
+        kernels the optimizer has produced."""
+        if self.stft.wsin.requires_grad or self.stft.wcos.requires_grad or self.n_fft != self._FUSED_N_FFT:
+            return True
         self._check_stft()
-        return (not self._stft_is_dft) or self.n_fft != self._FUSED_N_FFT or (
-            torch.is_grad_enabled() and (self.stft.wsin.requires_grad or self.stft.wcos.requires_grad))
+        return not self._stft_is_dft
 
     def output_shape(self, x_shape):
         return (x_shape[0], self.n_fft, x_shape[2] // self.hop_length + 1)
 
     def _check_input(self, x):
-        self._check_stft()
         if not isinstance(x, torch.Tensor) or x.dim() != 5 or x.shape[1] != 3:
             raise ValueError("expected x of shape (batch, 3, timesteps, vertices, num_graphs), got %s"
                              % (tuple(x.shape) if isinstance(x, torch.Tensor) else type(x),))
         if x.dtype != torch.float32:
             raise ValueError("VirtualRadar computes in float32 like the reference; got %s" % x.dtype)
+
+    def _check_device(self, x):
+        if not x.is_cuda:
+            raise RuntimeError("VirtualRadar (B200) has no CPU path: move x to a CUDA device, or call "
+                               "forward_host(x) to stream a pinned host batch through the GPU")
+        lam, loc = self.wavelength, self.radar_location
+        if lam.device != x.device or loc.device != x.device:
+            raise RuntimeError("module parameters are on %s but x is on %s; call .to(x.device)" % (lam.device, x.device))
+        return lam, loc
 
     def _prepare(self, x):
         """Pick the range rounding mode from the caller's strides BEFORE normalising the layout
@@ -242,12 +264,7 @@ class VirtualRadar(torch.nn.Module):
 
     def forward(self, x):
         self._check_input(x)
-        if not x.is_cuda:
-            raise RuntimeError("VirtualRadar (B200) has no CPU path: move x to a CUDA device, or call "
-                               "forward_host(x) to stream a pinned host batch through the GPU")
-        lam, loc = self.wavelength, self.radar_location
-        if lam.device != x.device or loc.device != x.device:
-            raise RuntimeError("module parameters are on %s but x is on %s; call .to(x.device)" % (lam.device, x.device))
+        lam, loc = self._check_device(x)
         xc, flags = self._prepare(x)
         if self._general_stft():     # trained / trainable STFT kernels: synthesis on our kernels, STFT as a GEMM
             if xc.shape[2] <= max(self.n_fft, self._FUSED_N_FFT) // 2:
@@ -267,11 +284,7 @@ class VirtualRadar(torch.nn.Module):
         that writes (N, 1, image_size, image_size) directly and transforms only the frames the
         resize keeps."""
         self._check_input(x)
-        if not x.is_cuda:
-            raise RuntimeError("VirtualRadar (B200) has no CPU path: move x to a CUDA device")
-        lam, loc = self.wavelength, self.radar_location
-        if lam.device != x.device or loc.device != x.device:
-            raise RuntimeError("module parameters are on %s but x is on %s; call .to(x.device)" % (lam.device, x.device))
+        lam, loc = self._check_device(x)
         image_size = int(image_size)
         if image_size < 1:
             raise ValueError("image_size must be positive, got %d" % image_size)
@@ -300,11 +313,7 @@ class VirtualRadar(torch.nn.Module):
         vr_forward_upsampled_f32; replaces reference utils.py:128-140 + layers/virtual_radar.py:79-134
         [+ models/resnet.py:24-26])."""
         self._check_input(x)
-        if not x.is_cuda:
-            raise RuntimeError("VirtualRadar (B200) has no CPU path: move x to a CUDA device")
-        lam, loc = self.wavelength, self.radar_location
-        if lam.device != x.device or loc.device != x.device:
-            raise RuntimeError("module parameters are on %s but x is on %s; call .to(x.device)" % (lam.device, x.device))
+        lam, loc = self._check_device(x)
         xc = x.contiguous()
         N, _, T, V, M = xc.shape
         k = int(num_pad_frames)
@@ -338,6 +347,7 @@ class VirtualRadar(torch.nn.Module):
     def forward_debug(self, x):
         """forward plus the intermediate complex baseband signal (N,T,2); for stage-level parity tests."""
         self._check_input(x)
+        self._check_device(x)
         xc, flags = self._prepare(x)
         return self._launch(xc, flags, want_iq=True)
 
@@ -355,6 +365,9 @@ class VirtualRadar(torch.nn.Module):
         N, _, T, V, M = xc.shape
         if out is None:
             out = torch.empty(self.output_shape(xc.shape), dtype=torch.float32, pin_memory=True)
+        elif (not isinstance(out, torch.Tensor) or out.is_cuda or out.dtype != torch.float32 or not out.is_contiguous()
+              or tuple(out.shape) != tuple(self.output_shape(xc.shape))):
+            raise ValueError("out must be a contiguous float32 CPU tensor of shape %s" % (tuple(self.output_shape(xc.shape)),))
         if N == 0:
             return out
         dev = torch.device(device) if device is not None else self.wavelength.device

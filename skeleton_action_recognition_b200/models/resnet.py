@@ -14,37 +14,57 @@ from torch import nn
 from ..layers.virtual_radar import VirtualRadar
 
 
-class _Block(nn.Module):
-    """Two 3x3 convolutions with an identity / 1x1-projection shortcut."""
+class BasicBlock(nn.Module):
+    """Two 3x3 convolutions with an identity / 1x1-projection shortcut.  Sub-module names (`conv1`, `bn1`, `conv2`,
+    `bn2`, `downsample.0/1`) are those of the reference's block (models/resnet18.py:36-76), so checkpoints interchange."""
 
     def __init__(self, cin, cout, stride):
         super().__init__()
-        self.body = nn.Sequential(
-            nn.Conv2d(cin, cout, 3, stride, 1, bias=False), nn.BatchNorm2d(cout), nn.ReLU(inplace=True),
-            nn.Conv2d(cout, cout, 3, 1, 1, bias=False), nn.BatchNorm2d(cout))
-        self.shortcut = None
+        self.conv1 = nn.Conv2d(cin, cout, 3, stride, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(cout)
+        self.relu = nn.ReLU(inplace=True)
+        self.conv2 = nn.Conv2d(cout, cout, 3, 1, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(cout)
+        self.downsample = None
         if stride != 1 or cin != cout:
-            self.shortcut = nn.Sequential(nn.Conv2d(cin, cout, 1, stride, bias=False), nn.BatchNorm2d(cout))
+            self.downsample = nn.Sequential(nn.Conv2d(cin, cout, 1, stride, bias=False), nn.BatchNorm2d(cout))
 
     def forward(self, x):
-        return torch.relu(self.body(x) + (x if self.shortcut is None else self.shortcut(x)))
+        y = self.bn2(self.conv2(self.relu(self.bn1(self.conv1(x)))))
+        return self.relu(y + (x if self.downsample is None else self.downsample(x)))
+
+
+class ResNet18(nn.Module):
+    """ResNet-18 over single-channel images with the reference's layout and parameter names (models/resnet18.py:131-185,
+    218-232: `conv1` 7x7/2 on 1 channel, `bn1`, 3x3/2 max-pool, `layer1..4` of two blocks with widths
+    num_filters * (1, 2, 4, 8), global average pool, `fc`): `state_dict()` keys and shapes equal the reference's, so a
+    checkpoint of the reference `Model` loads into `Model` here and vice versa (tests/test_feeder.py)."""
+
+    def __init__(self, num_classes=60, num_filters=64):
+        super().__init__()
+        w = num_filters
+        self.conv1 = nn.Conv2d(1, w, 7, 2, 3, bias=False)
+        self.bn1 = nn.BatchNorm2d(w)
+        self.relu = nn.ReLU(inplace=True)
+        self.maxpool = nn.MaxPool2d(3, 2, 1)
+        cin = w
+        for i, cout in enumerate((w, 2 * w, 4 * w, 8 * w)):
+            setattr(self, "layer%d" % (i + 1), nn.Sequential(BasicBlock(cin, cout, 1 if i == 0 else 2), BasicBlock(cout, cout, 1)))
+            cin = cout
+        self.avgpool = nn.AdaptiveAvgPool2d(1)
+        self.fc = nn.Linear(cin, num_classes)
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+
+    def forward(self, x):
+        x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
+        x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
+        return self.fc(torch.flatten(self.avgpool(x), 1))
 
 
 def resnet18(num_classes=60, num_filters=64):
-    """ResNet-18 over single-channel images: 7x7/2 stem, 3x3/2 max-pool, four stages of two blocks with
-    widths num_filters * (1, 2, 4, 8), global average pool, linear head."""
-    w = num_filters
-    layers = [nn.Conv2d(1, w, 7, 2, 3, bias=False), nn.BatchNorm2d(w), nn.ReLU(inplace=True), nn.MaxPool2d(3, 2, 1)]
-    cin = w
-    for i, cout in enumerate((w, 2 * w, 4 * w, 8 * w)):
-        layers += [_Block(cin, cout, 1 if i == 0 else 2), _Block(cout, cout, 1)]
-        cin = cout
-    layers += [nn.AdaptiveAvgPool2d(1), nn.Flatten(), nn.Linear(cin, num_classes)]
-    net = nn.Sequential(*layers)
-    for m in net.modules():
-        if isinstance(m, nn.Conv2d):
-            nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
-    return net
+    return ResNet18(num_classes, num_filters)
 
 
 class Model(nn.Module):

@@ -65,3 +65,25 @@ def golden_cases():
     out["offaxis"] = (x, dict(edges=[tuple(e) for e in z["edges"].tolist()], wavelength=1e-3,
                               radar_location=z["radar_location"].tolist()), z["y"], z["iq"])
     return out
+
+
+GAIT_EDGES = [(0, 1), (1, 2), (1, 3), (3, 5), (5, 7), (1, 4), (4, 6), (6, 8), (0, 9),
+              (9, 11), (11, 13), (13, 15), (0, 10), (10, 12), (12, 14), (14, 16)]
+
+# BASELINE configs 1 and 3 at FULL size: notebook cell, known-answer row of BASELINE.md section 3, up-sampling factor
+FULL = {"ntu": dict(row="B", pad=550, scale=1.0, kw=dict(edges=NTU_EDGES, wavelength=9e-4)),
+        "cmu": dict(row="C", pad=20, scale=0.001, kw=dict(edges=[(i, i + 1) for i in range(41)], wavelength=5e-3)),
+        "gait": dict(row="D", pad=10, scale=1.0, kw=dict(edges=GAIT_EDGES, wavelength=5e-4))}
+
+
+def full_case(name):
+    """The notebook's input of cells 4 / 2 / 3 rebuilt from the committed raw arrays (tests/golden/full_inputs.npz):
+    pad_frames (reference utils.py:82-89, scipy float64) -> transpose(2,0,1) -> expand_dims -> torch.Tensor, i.e.
+    (1,3,T,V,1) float32 with the coordinate axis innermost.  Returns (x, layer kwargs, golden dict)."""
+    c = FULL[name]
+    raw = load("full_inputs.npz")[name].astype(np.float64) if name == "cmu" else load("full_inputs.npz")[name]
+    x = notebook_tensor(pad_frames(raw * c["scale"] if c["scale"] != 1.0 else raw, num_pad_frames=c["pad"]))
+    g = load("full_outputs.npz")
+    gold = {"y": g[name + "_y"], "iq": g[name + "_iq"], "rowsum": g[name + "_rowsum"], "stride": int(g["stride"]),
+            "x_strides": tuple(int(s) for s in g[name + "_x_strides"])}
+    return x, c["kw"], gold

@@ -157,6 +157,36 @@ def test_trainable_stft_kernels():
     assert (xg.grad - xf.grad).abs().max() <= 2e-3 * scale
 
 
+def test_eval_after_training_uses_the_trained_stft_kernels():
+    """train_stft_kernel=True: one optimizer step, then an eval pass under no_grad must run the STFT against the UPDATED
+    stft.wsin/wcos (never the fused analytic FFT), and so must in-place edits and the frozen copy of such a model."""
+    x = fx.s3_smooth(3, T=300).cuda()
+    layer = _layer(wavelength=5e-3, train_stft_kernel=True)
+    opt = torch.optim.SGD(layer.parameters(), lr=5.0)
+    before = layer.stft.wsin.detach().clone()
+    layer(x).square().mean().backward()
+    opt.step()
+    assert not torch.equal(before, layer.stft.wsin.detach())
+    with torch.no_grad():
+        got = layer(x)
+        iq = layer.forward_debug(x)[1]
+        want = layer.stft.logmag(iq)
+    assert torch.equal(got, want)
+    fused = _layer(wavelength=5e-3)(x)
+    assert (got - fused).abs().max() > 1e-3                        # the trained kernels were really used
+    # a frozen layer whose kernels are edited in place through the parameters re-checks them (version counters)
+    frozen = _layer(wavelength=5e-3)
+    with torch.no_grad():
+        assert torch.equal(frozen(x), fused)
+        frozen.stft.wsin.copy_(layer.stft.wsin)
+        frozen.stft.wcos.copy_(layer.stft.wcos)
+        assert torch.equal(frozen(x), got)
+        frozen.stft.wsin.data.copy_(before)                        # through .data: no version bump -> explicit invalidation
+        frozen.stft.wcos.data.copy_(_layer(wavelength=5e-3).stft.wcos)
+        frozen.invalidate_stft_cache()
+        assert torch.equal(frozen(x), fused)
+
+
 @pytest.mark.parametrize("kw", [dict(wavelength=5e-3), dict(wavelength=1e-3, radar_location=[0.3, -0.2, 1.5])])
 def test_gradient_wrt_the_skeleton_data(kw):
     """dL/dx against float32 autograd over the reference graph (per-sequence l2 scale, 1e-3), an absent body gets 0

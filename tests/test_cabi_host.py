@@ -52,6 +52,25 @@ def test_plan_ntu(cabi):
     assert p["tma_loads"] == 0
 
 
+def test_plan_team(cabi):
+    """Team-job schedule (vr_team_kernel), host-only: two CTAs per SM, a two-stage ring per team whose stages can hold
+    the output tile, picked automatically only for batches with several sequences per team slot."""
+    from skeleton_action_recognition_b200 import edges
+    src, dst = map(list, zip(*edges))
+    p = cabi.plan_team(16384, 300, 25, 2, src, dst)
+    assert p["grid"] == 296 and p["block"] == 320 and p["teams_per_cta"] == 2 and p["ring_stages_per_team"] == 2
+    assert p["smem_bytes"] <= 233472 // 2 - 1024
+    assert p["stage_bytes"] >= max(3 * 32 * 50 * 4, 256 * 19 * 4) and p["stage_bytes"] % 128 == 0
+    assert p["z_stride"] >= 300 * 8 and p["automatic"] == 1
+    assert cabi.plan_team(256, 300, 25, 2, src, dst)["automatic"] == 0
+    assert cabi.plan_team(256, 300, 25, 2, src, dst)["grid"] == 128
+    assert cabi.plan_team(7, 300, 25, 2, src, dst)["grid"] == 4
+    assert cabi.plan_team(4, 300, 25, 1, src, dst)["grid"] == 2                # odd M: scalar twin
+    for bad in ((4, 165000, 25, 1), (4, 301, 25, 1), (4, 400, 25, 2)):       # several jobs / no TMA loads / 26 frames: no single bulk store
+        with pytest.raises(NotImplementedError):
+            cabi.plan_team(*bad, src, dst)
+
+
 def test_plan_image(cabi):
     """Launch plan of the fused resize (vr_forward_image_f32), host-only."""
     from skeleton_action_recognition_b200 import edges
@@ -138,7 +157,16 @@ def test_module_surface_matches_reference():
     assert tk.stft.wsin.requires_grad and tk.stft.wcos.requires_grad and not tk.wavelength.requires_grad
     assert tk._general_stft()                      # trainable kernels: synthesis kernel + GEMM STFT
     with torch.no_grad():
-        assert not tk._general_stft()              # analytic kernels, no gradient wanted: the fused FFT path
+        assert tk._general_stft()                  # ... also for an eval pass: the optimizer may have moved the kernels
+    # in-place edits through the parameters are seen (version counters), without a load_state_dict in between
+    ed = VirtualRadar(device="cpu")
+    assert not ed._general_stft()
+    with torch.no_grad():
+        ed.stft.wcos.mul_(1.5)
+    assert ed._general_stft()
+    with torch.no_grad():
+        ed.stft.wcos.copy_(layer.stft.wcos)
+    assert not ed._general_stft()
     import copy, pickle
     c = copy.deepcopy(layer)
     assert c.src == layer.src

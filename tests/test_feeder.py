@@ -2,6 +2,7 @@
 and labels from the reference's file formats (CPU tests); on the GPU the up-sampled batches equal what the
 reference's `Dataset.__getitem__` produces (oracle.pad_frames.dataset_getitem = scipy, as in utils.py:128-140),
 and `models.resnet.Model` is VirtualRadar -> unsqueeze -> nearest resize -> classifier (models/resnet.py:23-28)."""
+import os
 import pickle
 
 import numpy as np
@@ -61,6 +62,24 @@ def test_gpu_batches_equal_reference_getitem(tmp_path):
     assert tuple(raw.shape) == (3, 3, 48, 25, 2)
 
 
+def test_model_state_dict_matches_the_reference_model():
+    """Keys and shapes of `Model.state_dict()` are those of the reference's `models/resnet.py` Model: the classifier
+    (models/resnet18.py, recorded by loading that file by path in the build container; tests/golden/
+    resnet18_state_dict_f16.json for num_filters=16) under `base_model.`, the radar layer's four entries under
+    `virtual_radar.` -- so checkpoints of the reference load here and the other way round."""
+    import json
+    from skeleton_action_recognition_b200.models.resnet import Model
+    want = {"base_model." + k: tuple(v) for k, v in
+            json.load(open(os.path.join(os.path.dirname(__file__), "golden", "resnet18_state_dict_f16.json"))).items()}
+    want.update({"virtual_radar.wavelength": (), "virtual_radar.radar_location": (3,),
+                 "virtual_radar.stft.wsin": (256, 1, 256), "virtual_radar.stft.wcos": (256, 1, 256)})
+    model = Model(num_classes=60, num_filters=16, device="cpu")
+    got = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    assert got == want
+    twin = Model(num_classes=60, num_filters=16, device="cpu")
+    twin.load_state_dict(model.state_dict())                      # strict
+
+
 @pytest.mark.gpu
 def test_model_is_radar_resize_classifier():
     from skeleton_action_recognition_b200.models.resnet import Model
@@ -79,7 +98,7 @@ def test_model_is_radar_resize_classifier():
     loss = torch.nn.functional.cross_entropy(model(x), torch.tensor([1, 2, 3], device="cuda"))
     loss.backward()
     opt.step()
-    assert torch.isfinite(loss) and model.base_model[0].weight.grad is not None
+    assert torch.isfinite(loss) and model.base_model.conv1.weight.grad is not None
     assert sorted(k for k in model.state_dict() if k.startswith("virtual_radar")) == [
         "virtual_radar.radar_location", "virtual_radar.stft.wcos", "virtual_radar.stft.wsin", "virtual_radar.wavelength"]
 
