@@ -202,10 +202,11 @@ int vr_selftest_rounding(uint64_t n, float wavelength, uint64_t mismatches[3]);
 int vr_set_tuning(int warps, int ctas_per_sm, int stages);
 
 /* Benchmark knob (process-wide): which of the two schedules of the fused forward kernel a launch takes.  -1 (default)
- * automatic: batches with at least three sequences per team slot (592 on a B200) run the team-job schedule -- every
- * team of 4 warps owns a whole sequence, no CTA-wide barriers -- smaller ones the cooperative schedule (both teams of
- * a CTA share a sequence: half the latency per sequence); 0: always cooperative; 1: team jobs whenever the shape
- * qualifies (one job per sequence, plain output, TMA-loadable chunks).  The results are bit-identical.             */
+ * automatic: batches with at least three sequences per team slot (592 on a B200), and all launches flagged
+ * VR_FLAG_INPUTS_READY, run the team-job schedule -- every team of 4 warps owns a whole sequence, no CTA-wide
+ * barriers -- smaller stream-ordered ones the cooperative schedule (both teams of a CTA share a sequence: half the
+ * latency per sequence); 0: always cooperative; 1: team jobs whenever the shape qualifies (one job per sequence,
+ * plain output, TMA-loadable chunks).  The results are bit-identical.                                              */
 int vr_set_schedule(int mode);
 
 /* Profiling aid (process-wide; NULL = off, the default): when set, every CTA of subsequent launches
