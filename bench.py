@@ -7,18 +7,30 @@
 One "step" = one pass of the hot path over one batch of BASELINE config 2
 (N=256 NTU-shaped sequences, 3x300x25x2 -> 256x19) per GPU, synthetic input.
 
-  value      sequences/s, whole job, inputs already resident in HBM, one fused kernel launch per
-             step, CUDA events on the launching stream, barrier + synchronize on both sides, max
-             over ranks.  Steps rotate over a pool of input/output buffers larger than the 126 MB L2.
-  e2e        the same metric through the public API with HOST buffers: VirtualRadar.forward_host
-             (C ABI vr_forward_host_f32): pinned host input -> H2D -> kernel -> D2H inside the timed region.
-  roofline   HBM bound: algorithmic bytes per launch (199456 B/spectrogram x 256) over
-             the mean launch duration measured here; peak from MEASURED_PEAKS.json (else fallback).
-  cpu_baseline  the oracle port (reference algorithm, CPU PyTorch, all host threads) timed on this
-             box's host cores on a bounded sample (rank 0, N=1 only).
+Every device-timed figure is measured the same way (`timed_reps`): the K-step loop -- bracketed by a barrier +
+synchronize on both sides, CUDA events on the launching stream, max over ranks -- is REPEATED until at least 50 ms
+have been timed, and the median repetition is reported; K=20 steps of a 15 us kernel alone would be a 0.3 ms sample.
+
+  value          sequences/s, whole job, inputs resident in HBM, one fused launch per step, steps = independent batches
+                 in distinct buffers (a pool larger than the 126 MB L2) launched with VR_FLAG_INPUTS_READY, so that
+                 consecutive launches overlap (reads of step k+1 may start while step k's last CTAs finish; writes wait).
+  stream_ordered the same loop in plain stream order -- what `VirtualRadar.forward` does by default.
+  module_forward the drop-in module itself (`layer(x)`: checks, torch.empty, ctypes, launch), eager and as a CUDA graph.
+  e2e            the same metric through the public API with HOST buffers: VirtualRadar.forward_host
+                 (C ABI vr_forward_host_f32): pinned host input -> H2D -> kernel -> D2H inside the timed region.
+  roofline       HBM bound: algorithmic bytes per launch (199456 B/spectrogram x 256) over the mean launch
+                 duration measured here; peak from MEASURED_PEAKS.json (else the profiling guide's fallback).
+  large_batch    one launch over 16384 sequences per GPU (the sustained figure).
+  sweep          BASELINE config 4: global batches of 1k..64k sequences SHARDED by sequence over the ranks
+                 (shard_bounds = DataParallel's split, main_spectrogram.py:118-119): aggregate rate per global N.
+  shard_verify   (N > 1) a sharded batch, all-gathered over NCCL, is bit-identical to rank 0's single-GPU result.
+  train_step     BASELINE config 5 (1 GPU): main_spectrogram.py:146-158's step -- Model = fused radar input stage +
+                 ResNet-18 (reference layout), batch 64, forward + backward + Adam -- with the input stage's share.
+  cpu_baseline   the oracle port (reference algorithm, CPU PyTorch, all host threads) on this box's host cores.
   --impl reference   times only that CPU port, in the same JSON shape.
 """
 import argparse
+import hashlib
 import json
 import os
 import sys
@@ -37,6 +49,7 @@ BYTES_PER_SPEC = BYTES_IN + BYTES_OUT             # 199 456  
 FLOPS_PER_SPEC = 55 * T * 24 * M + F * (5 * N_FFT * 8 + 8 * N_FFT)   # 1 025 472
 WAVELENGTH = 5e-4
 WORKLOAD = "synthetic NTU-60 batch N=256, C=3, T=300, V=25, M=2 (BASELINE configs[1]), wavelength 5e-4, default 24-bone skeleton"
+MIN_TIMED_MS = 50.0
 
 
 def synth_batch(n, seed):
@@ -55,13 +68,29 @@ def measured_peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic():
-    """dram bytes per launch from the committed ncu --set full capture, if any (profiles/traffic.json)."""
+def source_hash():
+    """Hash of the kernel sources + header: ties a committed ncu capture to the build it was taken on."""
+    h = hashlib.sha256()
+    base = os.path.join(ROOT, "skeleton_action_recognition_b200", "csrc")
+    for name in sorted(os.listdir(base)):
+        with open(os.path.join(base, name), "rb") as f:
+            h.update(name.encode() + b"\0" + f.read())
+    with open(os.path.join(ROOT, "include", "virtual_radar_b200.h"), "rb") as f:
+        h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def ncu_traffic(kernel_key):
+    """dram bytes per launch from the committed `ncu --set full` capture (profiles/traffic.json, written by
+    tools/ncu_summary.py) -- only if it was taken on THIS build of the kernels; otherwise null and the reason."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f).get("dram_bytes_per_launch_n256")
+            t = json.load(f)
     except Exception:
-        return None
+        return None, "no committed capture"
+    if t.get("source_hash") != source_hash():
+        return None, "committed capture is of build %s, this is %s" % (t.get("source_hash"), source_hash())
+    return t.get(kernel_key), t.get("source")
 
 
 class ClockSampler(threading.Thread):
@@ -136,7 +165,7 @@ def time_cpu_port(n_seq, repeats, warmup=0):
 
 def run_reference(args, rank, world):
     """--impl reference: only rank 0 works; each step is a bounded sample of the workload sized so
-    that warmup+steps finish in about two minutes (the CPU path does ~70-100 spectrograms/s)."""
+    that warmup+steps finish in about two minutes (the CPU path does ~70-140 spectrograms/s)."""
     if rank != 0:
         return
     import torch
@@ -151,7 +180,7 @@ def run_reference(args, rank, world):
             "unit": "spectrograms/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample_per_step": n_seq,
+            "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "sample_per_step": n_seq,
                        "note": "reference algorithm on CPU PyTorch (oracle port of layers/virtual_radar.py + nnAudio STFT restatement); rank 0 only"},
             "cpu_baseline": {"value": value, "unit": "spectrograms/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "spectrograms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -163,11 +192,12 @@ def run_reference(args, rank, world):
 # our arm
 # ----------------------------------------------------------------------------------------------
 def run_ours(args, rank, world, local_rank):
+    import ctypes
     import torch
     import torch.distributed as dist
     import __graft_entry__ as ge
     ge.build_product()
-    from skeleton_action_recognition_b200 import VirtualRadar, _cabi
+    from skeleton_action_recognition_b200 import VirtualRadar, _cabi, shard_bounds
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
@@ -180,12 +210,39 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def max_over_ranks(v):
+    def max_over_ranks(values):
         if world == 1:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device=dev)
+            return list(values)
+        t = torch.tensor(list(values), dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return [float(v) for v in t.tolist()]
+
+    stream = torch.cuda.current_stream(dev)
+    launches = [0]
+
+    def timed_reps(step, k, min_ms=MIN_TIMED_MS, max_reps=400, warm=3):
+        """Median (over repetitions, after max over ranks) milliseconds of a k-step loop; repetitions until >= min_ms
+        have been timed.  Each repetition is bracketed by barrier + synchronize; CUDA events on the launching stream."""
+        for i in range(warm):
+            step(i)
+        barrier()
+        reps, total, times = 0, 0.0, []
+        while reps < 3 or (total < min_ms and reps < max_reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            e0.record(stream)
+            for i in range(k):
+                step(i)
+            e1.record(stream)
+            barrier()
+            ms = e0.elapsed_time(e1)
+            if world > 1:   # every rank must take the same number of repetitions: decide on the slowest rank's clock
+                ms = max_over_ranks([ms])[0]
+            times.append(ms)
+            total += ms
+            reps += 1
+        times.sort()
+        return times[len(times) // 2], reps, total
 
     layer = VirtualRadar(wavelength=WAVELENGTH, device=dev).to(dev)
     # pool of distinct batches bigger than L2 (126 MB): 6 x (46.1 + 5.0) MB = 306 MB
@@ -193,63 +250,77 @@ def run_ours(args, rank, world, local_rank):
     xs = [synth_batch(BATCH, 1000 * rank + i).to(dev) for i in range(pool)]
     outs = [torch.empty(BATCH, N_FFT, F, device=dev) for _ in range(pool)]
     lib = _cabi.lib()
-    import ctypes
-    stream = torch.cuda.current_stream(dev)
     s_ptr = ctypes.c_void_p(stream.cuda_stream)
     lam_ptr, loc_ptr = layer.wavelength.data_ptr(), layer.radar_location.data_ptr()
     E = len(layer.src)
+    K = max(1, args.steps)
 
-    # The steps are independent batches in distinct buffers, so the caller's guarantee VR_FLAG_INPUTS_READY holds: the
-    # launches are programmatic dependent launches and a step's READS may begin while the previous step's last CTAs
-    # are still running (its writes still wait).  Every step is computed in full; `stream_ordered` below is the same
-    # loop without the flag (each step waits for the previous one to finish completely).
-    def step(i, flags=_cabi.VR_FLAG_INPUTS_READY):
+    def raw_step(i, flags):
         # the module's forward minus torch.empty: the same C-ABI call on preallocated buffers
         rc = lib.vr_forward_f32(xs[i % pool].data_ptr(), BATCH, T, V, M, layer._src_c, layer._dst_c, E,
                                 lam_ptr, loc_ptr, N_FFT, HOP, flags, outs[i % pool].data_ptr(), s_ptr)
         if rc:
             _cabi.check(rc)
+        launches[0] += 1
 
     sampler = ClockSampler(physical_gpu_index(local_rank))
     sampler.start()
+    peak, peak_src = measured_peaks()
+    frac = lambda n, ms: BYTES_PER_SPEC * n / (ms * 1e-3) / 1e9 / peak     # noqa: E731
 
-    # ---- device-resident throughput ---------------------------------------------------------
+    # ---- headline: device-resident throughput, independent batches ----------------------------
     for i in range(max(args.warmup, 3)):
-        step(i)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        raw_step(i, _cabi.VR_FLAG_INPUTS_READY)
     sampler.active.set()
-    e0.record(stream)
-    for i in range(args.steps):
-        step(i)
-    e1.record(stream)
-    barrier()
+    launches[0] = 0
+    ms_k, reps, timed_ms = timed_reps(lambda i: raw_step(i, _cabi.VR_FLAG_INPUTS_READY), K, warm=0)
+    gpu_launches = launches[0]
     sampler.active.clear()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    ms_per_step = ms_total / args.steps
-    value = world * BATCH * args.steps / (ms_total * 1e-3)
+    ms_per_step = ms_k / K
+    value = world * BATCH / (ms_per_step * 1e-3)
     # correctness guard: the timed launches produced the same bits as the module's forward
     torch.cuda.synchronize(dev)
-    last = (args.steps - 1) % pool
-    for i in {0, last, (last + 1) % pool}:
+    for i in {0, (K - 1) % pool, K % pool}:
         assert torch.equal(outs[i], layer(xs[i])), "timed path != VirtualRadar.forward"
-    # the same loop in plain stream order (no overlap between consecutive steps)
-    so_steps = max(3, min(args.steps, 500))
-    for i in range(3):
-        step(i, 0)
-    barrier()
-    o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    o0.record(stream)
-    for i in range(so_steps):
-        step(i, 0)
-    o1.record(stream)
-    barrier()
-    so_ms = max_over_ranks(o0.elapsed_time(o1)) / so_steps
+
+    # ---- the same loop in plain stream order (what the module does by default) ----------------
+    sampler.active.set()
+    so_k, so_reps, _ = timed_reps(lambda i: raw_step(i, 0), K)
+    so_ms = so_k / K
+    # ---- the drop-in module itself: eager, and one forward captured in a CUDA graph ------------
+    holder = [None]
+
+    def module_step(i):
+        holder[0] = layer(xs[i % pool])
+    me_k, _, _ = timed_reps(module_step, K)
+    me_ms = me_k / K
+    static_x = xs[0].clone()
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(stream)
+    with torch.cuda.stream(side):
+        layer(static_x)
+    stream.wait_stream(side)
+    torch.cuda.synchronize(dev)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        static_y = layer(static_x)
+    mg_k, _, _ = timed_reps(lambda i: graph.replay(), K)
+    mg_ms = mg_k / K
+    assert torch.equal(static_y, layer(static_x))
+    sampler.active.clear()
+    module_forward = {
+        "eager": {"value": world * BATCH / (me_ms * 1e-3), "ms_per_step": me_ms, "hbm_frac": frac(BATCH, me_ms),
+                  "note": "layer(x) per step on the device-resident pool: input checks, torch.empty, ctypes call, one launch, plain stream order"},
+        "cuda_graph": {"value": world * BATCH / (mg_ms * 1e-3), "ms_per_step": mg_ms, "hbm_frac": frac(BATCH, mg_ms),
+                       "note": "one layer(x) captured with torch.cuda.graph and replayed (same buffers every step, so the batch stays in L2)"}}
+    del graph, static_x, static_y
 
     # ---- end to end through the public API with host buffers --------------------------------
     xh = [synth_batch(BATCH, 2000 * rank + i).pin_memory() for i in range(2)]
     oh = torch.empty(BATCH, N_FFT, F).pin_memory()
-    e2e_steps = max(3, min(args.steps, 200))
+    e2e_steps = max(3, min(K, 200))
+    while e2e_steps * 1.0 < MIN_TIMED_MS and e2e_steps < 200:      # ~1 ms per step: at least 50 ms
+        e2e_steps *= 2
     for i in range(3):
         layer.forward_host(xh[i % 2], out=oh)
     barrier()
@@ -260,42 +331,84 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize(dev)
     dt = time.perf_counter() - t0
     sampler.active.clear()
-    dt = max_over_ranks(dt)
+    dt = max_over_ranks([dt])[0]
     e2e_value = world * BATCH * e2e_steps / dt
     assert torch.equal(oh, layer(xh[(e2e_steps - 1) % 2].to(dev)).cpu()), "e2e path != VirtualRadar.forward"
+    del xh, oh
 
-    # ---- sustained large batch (same kernel, many jobs per CTA), for the roofline picture ----
+    # ---- sustained large batch (many jobs per team), for the roofline picture ----------------
     big_n = 16384
-    xb = synth_batch(256, 77).to(dev).repeat(big_n // 256, 1, 1, 1, 1)
+    base = synth_batch(256, 77 + rank).to(dev)
+    xb = base.repeat(big_n // 256, 1, 1, 1, 1)
     ob = torch.empty(big_n, N_FFT, F, device=dev)
 
-    def big_step():
+    def big_step(i):
         rc = lib.vr_forward_f32(xb.data_ptr(), big_n, T, V, M, layer._src_c, layer._dst_c, E, lam_ptr, loc_ptr,
                                 N_FFT, HOP, 0, ob.data_ptr(), s_ptr)
         if rc:
             _cabi.check(rc)
-    for _ in range(3):
-        big_step()
-    barrier()
     sampler.active.set()
-    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 40
-    b0.record(stream)
-    for _ in range(reps):
-        big_step()
-    b1.record(stream)
-    barrier()
+    big_k, _, _ = timed_reps(big_step, 10, min_ms=100.0)
     sampler.active.clear()
-    big_ms = max_over_ranks(b0.elapsed_time(b1)) / reps
+    big_ms = big_k / 10
     big_value = world * big_n / (big_ms * 1e-3)
+    del ob
+
+    # ---- BASELINE config 4: global batches sharded by sequence over the ranks -----------------
+    sweep = []
+    for gn in (1024, 4096, 16384, 65536):
+        lo, hi = shard_bounds(gn, world, rank)
+        n_loc = hi - lo
+        xsw = xb[:n_loc] if n_loc <= big_n else base.repeat((n_loc + 255) // 256, 1, 1, 1, 1)[:n_loc]
+        osw = torch.empty(max(n_loc, 1), N_FFT, F, device=dev)
+
+        def sw_step(i):
+            if n_loc > 0:
+                rc = lib.vr_forward_f32(xsw.data_ptr(), n_loc, T, V, M, layer._src_c, layer._dst_c, E, lam_ptr, loc_ptr,
+                                        N_FFT, HOP, 0, osw.data_ptr(), s_ptr)
+                if rc:
+                    _cabi.check(rc)
+        ksw = 8 if gn <= 4096 else 3
+        sw_k, _, _ = timed_reps(sw_step, ksw, min_ms=30.0)
+        sw_ms = sw_k / ksw
+        sweep.append({"global_n": gn, "per_rank": -(-gn // world), "ms": sw_ms, "value": gn / (sw_ms * 1e-3),
+                      "hbm_frac_per_gpu": frac(gn, sw_ms) / world})
+        del osw, xsw
+    # ---- shard verification: NCCL gathers the shards' outputs; nothing else crosses GPUs --------
+    shard_verify = None
+    if world > 1:
+        from skeleton_action_recognition_b200 import sharded_forward
+        vn = 1000                                      # not a multiple of the world size: ragged last shard
+        xv = synth_batch(256, 4242).to(dev).repeat(4, 1, 1, 1, 1)[:vn].contiguous()
+        xv[500:] *= 1.5
+        full = sharded_forward(layer, xv)
+        same = bool(torch.equal(full, layer(xv)))
+        flag = torch.tensor([1.0 if same else 0.0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        shard_verify = {"global_n": vn, "world": world, "bit_identical_to_single_gpu": bool(flag.item() == 1.0),
+                        "how": "shard_bounds split, each rank's fused launch, torch.distributed.all_gather_into_tensor (NCCL), torch.equal against the rank's own single-GPU result of the whole batch"}
+        assert shard_verify["bit_identical_to_single_gpu"], "sharded result differs from single GPU"
+        del xv, full
     sampler.stop()
 
-    peak, peak_src = measured_peaks()
     achieved = BYTES_PER_SPEC * BATCH / (ms_per_step * 1e-3) / 1e9
     big_achieved = BYTES_PER_SPEC * big_n / (big_ms * 1e-3) / 1e9
     props = torch.cuda.get_device_properties(dev)
     fp32_peak = props.multi_processor_count * 128 * 2 * 1.965e9 / 1e12
     plan = _cabi.plan(BATCH, T, V, M, layer.src, layer.dst, N_FFT, HOP, props.multi_processor_count)
+    plan_team = _cabi.plan_team(BATCH, T, V, M, layer.src, layer.dst, N_FFT, HOP, props.multi_processor_count)
+
+    def timed(fn, reps):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize(dev)
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record(stream)
+        for _ in range(reps):
+            fn()
+        t1.record(stream)
+        torch.cuda.synchronize(dev)
+        return t0.elapsed_time(t1) / reps
 
     # ---- the data loader's up-sampling pre-stage, reported beside the headline ----
     pre_stage = None
@@ -304,16 +417,7 @@ def run_ours(args, rank, world, local_rank):
         pn, pk = props.multi_processor_count, 250               # one (sequence, coordinate) plane per CTA, 3 waves
         px = synth_batch(pn, 99).to(dev)
         po = torch.empty(pn, 3, T * pk, V, M, device=dev)
-        for _ in range(2):
-            pad_frames(px, pk, out=po)
-        torch.cuda.synchronize(dev)
-        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        p0.record(stream)
-        for _ in range(5):
-            pad_frames(px, pk, out=po)
-        p1.record(stream)
-        torch.cuda.synchronize(dev)
-        pms = p0.elapsed_time(p1) / 5
+        pms = timed(lambda: pad_frames(px, pk, out=po), 5)
         pbytes = po.numel() * 4 + px.numel() * 4
         pre_stage = {"op": "pad_frames (Dataset.pad_frames + cast, utils.py:128-140), num_pad_frames=250, sigma=3",
                      "n": pn, "ms": pms, "value": pn / (pms * 1e-3), "unit": "sequences/s",
@@ -330,18 +434,8 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- the rows next to the headline path: fused consumer resize, fused up-sampling ----
     next_rows = None
+    train_step = None
     if rank == 0 and world == 1:
-        def timed(fn, reps):
-            for _ in range(2):
-                fn()
-            torch.cuda.synchronize(dev)
-            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            t0.record(stream)
-            for _ in range(reps):
-                fn()
-            t1.record(stream)
-            torch.cuda.synchronize(dev)
-            return t0.elapsed_time(t1) / reps
         img_n, S = 4096, 256
         xi = xb[:img_n]
         ms_f = timed(lambda: layer.forward_image(xi, S), 20)
@@ -367,6 +461,7 @@ def run_ours(args, rank, world, local_rank):
         # the same stage end to end from the loader's side: RAW pinned host batch -> H2D -> fused launch -> image on
         # the device (where the classifier consumes it); wall clock, copies inside the timed region
         uh = [synth_batch(un, 56 + i).pin_memory() for i in range(2)]
+
         def from_host(i):
             return layer.forward_upsampled(uh[i % 2].to(dev, non_blocking=True), uk, 3, image_size=S)
         for i in range(2):
@@ -383,6 +478,34 @@ def run_ours(args, rank, world, local_rank):
                     "the reference ships the 250x up-sampled batch (45 MB per sequence) over PCIe instead"}
         del ux, ubuf, uh, img
 
+        # ---- BASELINE config 5: the consumer's training step with the fused input stage ----------
+        from skeleton_action_recognition_b200.models.resnet import Model
+        tb = 64
+        labels = torch.randint(0, 60, (tb,), generator=torch.Generator().manual_seed(1)).to(dev)
+        train_step = {"op": "main_spectrogram.py:146-158: outputs = model(inputs); CrossEntropyLoss; backward; Adam step -- "
+                            "Model = VirtualRadar input stage + ResNet-18 (reference layout: 1 input channel, 64 filters, 60 classes), "
+                            "batch 64, image 256x256, float32, random-init weights, synthetic labels; the classifier is stock PyTorch/cuDNN",
+                      "batch": tb}
+        for name, kpad in (("radar_rate_input", None), ("raw_input_upsampled_x250", 250)):
+            model = Model(num_classes=60, num_filters=64, image_size=256, device=dev, num_pad_frames=kpad).to(dev)
+            opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+            xt = synth_batch(tb, 7).to(dev)
+
+            def one_step():
+                opt.zero_grad(set_to_none=True)
+                loss = torch.nn.functional.cross_entropy(model(xt), labels)
+                loss.backward()
+                opt.step()
+                return loss
+            ms_step = timed(one_step, 10)
+            with torch.no_grad():
+                ms_in = timed(lambda: model.spectrogram_image(xt), 10)
+            train_step[name] = {"ms_per_step": ms_step, "samples_per_s": tb / (ms_step * 1e-3),
+                                "input_stage_ms": ms_in, "input_stage_share": ms_in / ms_step,
+                                "input_frames_per_sequence": T * (kpad or 1)}
+            del model, opt, xt
+    del xb
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         times = time_cpu_port(BATCH, 3)
@@ -390,38 +513,45 @@ def run_ours(args, rank, world, local_rank):
                         "kind": "port", "sample": "the full N=256 batch once per repeat, best of 3 (%.2f s each)" % min(times)}
 
     if rank == 0:
+        traffic, traffic_src = ncu_traffic("dram_bytes_per_launch_n256")
         line = {
             "metric": "spectrograms/sec (NTU 3x300x25x2)", "value": value, "unit": "spectrograms/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "sharding": "by sequence, no collective on the path",
                        "l2": "steps rotate over %d input/output buffer pairs (%.0f MB > 126 MB L2)" % (pool, pool * BATCH * BYTES_PER_SPEC / 1e6),
-                       "launch": plan,
-                       "overlap": "steps are independent batches: programmatic dependent launches with VR_FLAG_INPUTS_READY "
-                                  "(a step's reads may start while the previous step's last CTAs finish; writes wait)"},
-            "stream_ordered": {"value": world * BATCH / (so_ms * 1e-3), "ms_per_step": so_ms, "steps": so_steps,
-                               "hbm_frac": BYTES_PER_SPEC * BATCH / (so_ms * 1e-3) / 1e9 / peak,
+                       "timing": "the %d-step loop repeated %d times (%.0f ms timed in total, >= %.0f ms), median repetition, max over ranks per repetition"
+                                 % (K, reps, timed_ms, MIN_TIMED_MS),
+                       "launch": {"cooperative": plan, "team_jobs": plan_team,
+                                  "schedule": "team jobs for overlapping or large batches, cooperative otherwise (vr_set_schedule)"},
+                       "overlap": "value: steps are independent batches, programmatic dependent launches with VR_FLAG_INPUTS_READY "
+                                  "(a step's reads may start while the previous step's last CTAs finish; writes wait); "
+                                  "stream_ordered: the same loop without the flag, the module's default"},
+            "stream_ordered": {"value": world * BATCH / (so_ms * 1e-3), "ms_per_step": so_ms, "steps": K, "reps": so_reps,
+                               "hbm_frac": frac(BATCH, so_ms),
                                "note": "same loop without the flag: every step waits for the previous kernel to finish"},
+            "module_forward": module_forward,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(), "peak_source": peak_src,
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": BYTES_PER_SPEC * BATCH,
                          "fp32_tflops": FLOPS_PER_SPEC * BATCH / (ms_per_step * 1e-3) / 1e12,
                          "fp32_frac_of_derived_peak": FLOPS_PER_SPEC * BATCH / (ms_per_step * 1e-3) / 1e12 / fp32_peak},
             "large_batch": {"n_per_gpu": big_n, "value": big_value, "ms_per_launch": big_ms,
                             "hbm_achieved_gbs": big_achieved, "hbm_frac": big_achieved / peak,
-                            "note": "same kernel, one launch over 16384 sequences per GPU (2.95 GB in, 0.32 GB out)"},
+                            "note": "one stream-ordered launch over 16384 sequences per GPU (2.95 GB in, 0.32 GB out)"},
+            "sweep": {"what": "BASELINE config 4: global batch sharded by sequence over %d rank(s), stream-ordered launches, aggregate sequences/s" % world,
+                      "points": sweep},
             "e2e": {"value": e2e_value, "unit": "spectrograms/s", "h2d_bytes_per_step": BATCH * BYTES_IN,
                     "d2h_bytes_per_step": BATCH * BYTES_OUT, "steps": e2e_steps,
                     "api": "VirtualRadar.forward_host (C ABI vr_forward_host_f32), pinned host buffers"},
-            "gpu_launches": args.steps,
+            "gpu_launches": gpu_launches,
+            "source_hash": source_hash(),
             "clocks": sampler.summary(),
         }
-        if cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline
-        if pre_stage:
-            line["pre_stage"] = pre_stage
-        if next_rows:
-            line["next_rows"] = next_rows
+        for key, val in (("shard_verify", shard_verify), ("cpu_baseline", cpu_baseline), ("pre_stage", pre_stage),
+                         ("next_rows", next_rows), ("train_step", train_step)):
+            if val:
+                line[key] = val
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -430,7 +560,7 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
