@@ -471,7 +471,7 @@ struct Staging {
     cudaStream_t st[2] = {nullptr, nullptr};
 };
 Staging g_stage[64];
-std::mutex g_stage_mu;
+std::mutex g_stage_mu[64];                        // one per device: host-pipelined calls on different devices do not serialise
 
 }  // namespace
 
@@ -566,7 +566,7 @@ int vr_forward_host_f32(const float* x_host, int64_t N, int64_t T, int32_t V, in
     }
     sub_batch = std::min<int64_t>(sub_batch, N);
     Staging& sg = g_stage[dev];
-    std::lock_guard<std::mutex> lk(g_stage_mu);   // one host-pipelined call per process at a time
+    std::lock_guard<std::mutex> lk(g_stage_mu[dev]);   // one host-pipelined call per device at a time (the staging buffers are per device)
     if (!sg.st[0]) {
         CUDA_TRY(cudaStreamCreateWithFlags(&sg.st[0], cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&sg.st[1], cudaStreamNonBlocking));
@@ -785,10 +785,10 @@ int backward_impl(const float* x_dev, const float* iq_dev, const float* grad_out
 extern "C" {
 
 int vr_release_host_staging(void) {
-    std::lock_guard<std::mutex> lk(g_stage_mu);
     int cur = 0;
     cudaGetDevice(&cur);
     for (int d = 0; d < 64; ++d) {
+        std::lock_guard<std::mutex> lk(g_stage_mu[d]);
         Staging& sg = g_stage[d];
         if (!sg.st[0] && !sg.x[0]) continue;
         cudaSetDevice(d);

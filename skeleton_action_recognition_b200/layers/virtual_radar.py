@@ -173,6 +173,7 @@ class VirtualRadar(torch.nn.Module):
         d = self.__dict__.copy()
         d.pop("_src_c", None)
         d.pop("_dst_c", None)
+        d.pop("_host_params", None)
         return d
 
     def __setstate__(self, d):
@@ -373,13 +374,24 @@ class VirtualRadar(torch.nn.Module):
         dev = torch.device(device) if device is not None else self.wavelength.device
         if dev.type != "cuda":
             dev = torch.device("cuda", torch.cuda.current_device())
-        loc = (ctypes.c_float * 3)(*[float(v) for v in self.radar_location.detach().cpu().tolist()])
+        lam, loc = self._host_parameters()
         with torch.cuda.device(dev):
             rc = _cabi.lib().vr_forward_host_f32(xc.data_ptr(), N, T, V, M, self._src_c, self._dst_c, len(self.src),
-                                                 ctypes.c_float(float(self.wavelength.detach().cpu())), loc,
+                                                 ctypes.c_float(lam), loc,
                                                  self.n_fft, self.hop_length, flags, out.data_ptr(), int(sub_batch))
         _cabi.check(rc)
         return out
+
+    def _host_parameters(self):
+        """Host copies of the two radar parameters for the host-buffer entry point, refreshed only when the parameters
+        change (identity / version counters) -- not two device-to-host synchronisations per call."""
+        key = tuple((t.data_ptr(), t._version, t.device) for t in (self.wavelength, self.radar_location))
+        cached = getattr(self, "_host_params", None)
+        if cached is None or cached[0] != key:
+            lam = float(self.wavelength.detach().cpu())
+            loc = (ctypes.c_float * 3)(*[float(v) for v in self.radar_location.detach().cpu().tolist()])
+            cached = self._host_params = (key, lam, loc)
+        return cached[1], cached[2]
 
     def extra_repr(self):
         return "bones=%d, n_fft=%d, hop_length=%d" % (len(self.src), self.n_fft, self.hop_length)
