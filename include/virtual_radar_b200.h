@@ -107,6 +107,18 @@ int vr_release_host_staging(void);
 int vr_pad_frames_f32(const float* x_dev, int64_t N, int64_t T, int32_t V, int32_t M, int32_t num_pad_frames,
                       float sigma, float* out_dev, void* stream);
 
+/* The notebook's variant of the up-sampling: replaces `utils.pad_frames` (reference utils.py:82-89, used by
+ * virtual_radar_example.ipynb cells 2-4 on one body's (T, V, C) array): scipy gaussian_filter1d(sigma) along the JOINT
+ * axis (axis=1 -- a quirk of the reference that is kept), then the not-a-knot cubic interp1d in time to
+ * num_pad_frames*T frames in float64, then the float32 cast of torch.Tensor(...).
+ *   x_dev (N, T, V, C) float64 (x_is_f64 != 0) or float32, contiguous; T >= 4, T <= 8500 (shared-memory spline solve).
+ *   out_dev float32: planar_out == 0: (N, num_pad_frames*T, V, C) -- permuted to (N, C, k*T, V, 1) this is the notebook's
+ *   coordinate-innermost tensor (strides (.., 1, V*C, C, C)), for which the layer picks VR_FLAG_RANGE_FMA itself;
+ *   planar_out != 0: (N, C, num_pad_frames*T, V) -- the layer's own input layout with M = 1, for a direct vr_forward_f32
+ *   call with VR_FLAG_RANGE_FMA and no layout copy in between.                                                        */
+int vr_pad_frames_joints(const void* x_dev, int32_t x_is_f64, int64_t N, int64_t T, int32_t V, int32_t C,
+                         int32_t num_pad_frames, float sigma, int32_t planar_out, float* out_dev, void* stream);
+
 /* The data loader's up-sampling fused in front of the layer: equals vr_pad_frames_f32 followed by
  * vr_forward_f32 (image_size == 0; out_dev is (N, n_fft, num_pad_frames*T/hop + 1)) or by
  * vr_forward_image_f32 (image_size > 0; out_dev is (N, 1, image_size, image_size)) bit for bit, but the

@@ -20,6 +20,10 @@ Variants:
                    by `distance_mode_for(x)`.
   forward(..., dtype=torch.float64)                    "truth-f64": same graph in double, with
         the float32-rounded parameter values.
+  forward_hybrid(...)                                   "hybrid": the rounding-critical range and phase exactly as the
+        float32 reference forms them, EVERYTHING ELSE in float64 (amplitudes, cos/sin of that float32 phase, sums, STFT,
+        log).  Separates the reference's phase rounding (which a faithful implementation must reproduce) from its
+        other float32 noise (which it need not): |ref-f32 - hybrid| is the floor any float32 implementation sits on.
 
 Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline leg, --impl reference) may
 import this module.  The product (skeleton_action_recognition_b200) never does.
@@ -193,6 +197,21 @@ def _f64_kernels(n_fft):
 def forward(x, edges=NTU_EDGES, wavelength=1e-3, radar_location=(0., 0., 0.), n_fft=256,
             hop_length=16, dtype=torch.float32, distance="aten"):
     return OracleVirtualRadar(edges, wavelength, radar_location, n_fft, hop_length, dtype)(x, distance)
+
+
+@torch.no_grad()
+def forward_hybrid(x, edges=NTU_EDGES, wavelength=1e-3, radar_location=(0., 0., 0.), n_fft=256, hop_length=16,
+                   distance="aten"):
+    """SURVEY 8c variant (3): float32 range / phase (bit-identical to the reference's), float64 everything else."""
+    src, dst = map(list, zip(*edges))
+    lam32 = torch.as_tensor(wavelength, dtype=torch.float32)
+    loc32 = torch.as_tensor(list(radar_location), dtype=torch.float32)
+    _, phase32 = bone_geometry(x, src, dst, loc32, lam32, distance)              # float32, the reference's rounding
+    amp64, _ = bone_geometry(x.double(), src, dst, loc32.double(), lam32.double())
+    ph = phase32.double()
+    iq = torch.stack((amp64 * torch.cos(ph), amp64 * torch.sin(ph)), dim=4).sum(dim=[2, 3])
+    o = OracleVirtualRadar(edges, wavelength, radar_location, n_fft, hop_length, torch.float64)
+    return stft_logmag(iq, o.stft, n_fft)
 
 
 # ---------------------------------------------------------------------------------------------

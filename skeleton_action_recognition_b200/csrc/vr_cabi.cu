@@ -662,6 +662,56 @@ int vr_pad_frames_f32(const float* x_dev, int64_t N, int64_t T, int32_t V, int32
     return pad_launch(x_dev, N, T, V, M, num_pad_frames, sigma, out_dev, nullptr, stream);
 }
 
+int vr_pad_frames_joints(const void* x_dev, int32_t x_is_f64, int64_t N, int64_t T, int32_t V, int32_t C,
+                         int32_t num_pad_frames, float sigma, int32_t planar_out, float* out_dev, void* stream) {
+    if (!x_dev || !out_dev) return fail(VR_ERR_ARG, "x_dev and out_dev must not be null");
+    if (N <= 0 || V <= 0 || C <= 0) return fail(VR_ERR_SHAPE, "N, V, C must be positive (got %lld, %d, %d)", (long long)N, V, C);
+    if (T < 4) return fail(VR_ERR_SHAPE, "T=%lld: cubic interpolation needs at least 4 frames (scipy interp1d raises ValueError)", (long long)T);
+    if (num_pad_frames < 1) return fail(VR_ERR_SHAPE, "num_pad_frames must be >= 1, got %d", num_pad_frames);
+    if (!(sigma > 0.f)) return fail(VR_ERR_SHAPE, "sigma must be positive, got %g", (double)sigma);
+    if ((double)T * num_pad_frames > 2.0e9) return fail(VR_ERR_UNSUPPORTED, "T*num_pad_frames too large");
+    int dev, sm_count;
+    int rc = device_setup(dev, sm_count);
+    if (rc) return rc;
+    vr::PadNbParams p;
+    memset(&p, 0, sizeof(p));
+    const double sd = (double)sigma;
+    p.radius = (int)(4.0 * sd + 0.5);
+    if (p.radius > vr::PF_MAX_RADIUS) return fail(VR_ERR_UNSUPPORTED, "sigma=%g needs a Gaussian radius of %d > %d", sd, p.radius, vr::PF_MAX_RADIUS);
+    {
+        double phi[2 * vr::PF_MAX_RADIUS + 1], sum = 0.0;
+        const double sigma2 = sd * sd;
+        for (int i = -p.radius; i <= p.radius; ++i) phi[i + p.radius] = exp(-0.5 / sigma2 * (double)(i * i));
+        for (int i = 0; i <= 2 * p.radius; ++i) sum += phi[i];
+        for (int j = 0; j <= p.radius; ++j) p.w[j] = phi[p.radius + j] / sum;
+    }
+    p.x = x_dev; p.out = out_dev; p.N = N; p.T = (int)T; p.V = V; p.C = C; p.K = num_pad_frames; p.planar = planar_out ? 1 : 0;
+    p.ratio = (double)(T - 1) / (double)((long long)num_pad_frames * T - 1);
+    const long long VC = (long long)V * C;
+    const long long budget = 200 * 1024 - 8ll * T;               // 16 bytes per (frame, column) + 8 per frame
+    long long nc = budget / (16ll * T);
+    if (nc < 1) return fail(VR_ERR_UNSUPPORTED, "T=%lld too long for the shared-memory spline solve (max %d frames)", (long long)T, 200 * 1024 / 24);
+    nc = std::min<long long>(std::min<long long>(nc, VC), 1024);
+    p.ncb = (int)((VC + nc - 1) / nc);
+    p.nc = (int)((VC + p.ncb - 1) / p.ncb);
+    const size_t smem = (size_t)p.T * p.nc * 16 + (size_t)p.T * 8 + 16;
+    static std::mutex mu;
+    static bool attr_done[64] = {false};
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!attr_done[dev]) {
+            CUDA_TRY(cudaFuncSetAttribute(vr::vr_pad_frames_nb_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            CUDA_TRY(cudaFuncSetAttribute(vr::vr_pad_frames_nb_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            attr_done[dev] = true;
+        }
+    }
+    const int grid = (int)std::min<long long>(N * p.ncb, (long long)sm_count * 4);
+    if (x_is_f64) vr::vr_pad_frames_nb_kernel<double><<<grid, 1024, smem, (cudaStream_t)stream>>>(p);
+    else vr::vr_pad_frames_nb_kernel<float><<<grid, 1024, smem, (cudaStream_t)stream>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    return VR_OK;
+}
+
 int64_t vr_upsampled_workspace_bytes(int64_t N, int64_t T, int32_t V, int32_t M) {
     if (N <= 0 || T < 2 || V <= 0 || M <= 0) return 0;
     return N * (T - 1) * 4 * 3 * (int64_t)V * M * (int64_t)sizeof(double);

@@ -161,4 +161,117 @@ __global__ void __launch_bounds__(1024, 1) vr_pad_frames_kernel(const __grid_con
 }
 #endif  // __CUDACC__
 
+// ------------------------------------------------------------------------------------------------
+// The notebook's variant: `utils.pad_frames` (reference utils.py:82-89), used by virtual_radar_example.ipynb
+// cells 2-4 on (T, V, C) arrays of ONE body:
+//
+//   smooth = scipy.ndimage.gaussian_filter1d(data, sigma, axis=1)     along the JOINT axis (a quirk that is kept,
+//                                                                    SURVEY Appendix D); same dtype out as in
+//   spline = scipy.interpolate.interp1d(linspace(0,1,T), smooth, 'cubic', axis=-3)     not-a-knot cubic in time, float64
+//   out    = spline(linspace(0,1,k*T))                                float64; the notebook then casts with torch.Tensor
+//
+// x: (N, T, V, C) float64 or float32 (both occur: the mocap files are float64, the NTU example float32).  Output
+// float32 -- the cast of torch.Tensor(...) -- in one of two layouts: ROWS (N, k*T, V, C), whose permuted view is exactly
+// the notebook's coordinate-innermost tensor, or PLANES (N, C, k*T, V), the layer's own input layout, for the fused
+// call that skips the layout copy (the range rounding mode then has to be passed explicitly: VR_FLAG_RANGE_FMA).
+// One CTA owns `nc` adjacent (joint, coordinate) columns of one sequence; everything between the Gaussian and the
+// evaluation stays in shared memory as float64: 16 bytes per (frame, column) + 8 per frame, i.e. T <= 8500 frames in
+// (the reference's three inputs have 300, 2751 and 8192).
+struct PadNbParams {
+    const void* x;               // (N, T, V, C), TIN
+    float* out;
+    long long N;
+    int T, V, C, K, nc, ncb, planar;
+    int radius;
+    double ratio;
+    double w[PF_MAX_RADIUS + 1];
+};
+
+#ifdef __CUDACC__
+template <typename TIN>
+__global__ void __launch_bounds__(1024, 1) vr_pad_frames_nb_kernel(const __grid_constant__ PadNbParams p) {
+    extern __shared__ __align__(16) unsigned char pf_smem[];
+    const int T = p.T, nc = p.nc, VC = p.V * p.C;
+    double* Msh = reinterpret_cast<double*>(pf_smem);            // [T][nc] second derivatives
+    double* ys = Msh + (size_t)T * nc;                           // [T][nc] smoothed trajectories (rounded to TIN like scipy's output)
+    double* cp = ys + (size_t)T * nc;                            // [T]     Thomas coefficients
+    const int tid = threadIdx.x;
+    const long long KT = (long long)p.K * T;
+
+    for (long long unit = blockIdx.x; unit < p.N * p.ncb; unit += gridDim.x) {
+        const long long n = unit / p.ncb;
+        const int col0 = (int)(unit - n * p.ncb) * nc;
+        const int ncl = (VC - col0 < nc) ? (VC - col0) : nc;
+        const TIN* xp = static_cast<const TIN*>(p.x) + n * (long long)T * VC;
+        __syncthreads();
+
+        // (1) Gaussian along the joints of every frame: scipy's correlate1d order (centre tap, then symmetric pairs
+        // from the outermost inwards), float64 accumulation, result rounded to the input dtype
+        for (int idx = tid; idx < T * ncl; idx += blockDim.x) {
+            const int t = idx / ncl, col = col0 + (idx - t * ncl);
+            const int v = col / p.C, c = col - v * p.C;
+            const TIN* row = xp + (size_t)t * VC + c;
+            double acc = __dmul_rn((double)row[v * p.C], p.w[0]);
+            for (int jj = p.radius; jj >= 1; --jj) {
+                const double a = (double)row[pf_reflect(v - jj, p.V) * p.C];
+                const double b = (double)row[pf_reflect(v + jj, p.V) * p.C];
+                acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(a, b), p.w[jj]));
+            }
+            ys[t * nc + (col - col0)] = (double)(TIN)acc;
+        }
+        if (tid == 0) {
+            double c = 0.0;
+            for (int i = 2; i <= T - 3; ++i) { c = 1.0 / (4.0 - c); cp[i] = c; }
+        }
+        __syncthreads();
+
+        // (2) not-a-knot cubic spline in time, one thread per column (same elimination as vr_pad_frames_kernel)
+        if (tid < ncl) {
+            const int c = tid;
+            auto rhs = [&](int i) { return 6.0 * ((ys[(i - 1) * nc + c] - 2.0 * ys[i * nc + c]) + ys[(i + 1) * nc + c]); };
+            const double M1 = rhs(1) / 6.0, Mn = rhs(T - 2) / 6.0;
+            Msh[1 * nc + c] = M1;
+            Msh[(T - 2) * nc + c] = Mn;
+            double d = 0.0;
+            for (int i = 2; i <= T - 3; ++i) {
+                double r = rhs(i);
+                if (i == 2) r -= M1;
+                if (i == T - 3) r -= Mn;
+                d = (r - d) * cp[i];
+                Msh[i * nc + c] = d;
+            }
+            double next = 0.0;
+            for (int i = T - 3; i >= 2; --i) {
+                const double m = Msh[i * nc + c] - (i == T - 3 ? 0.0 : cp[i] * next);
+                Msh[i * nc + c] = m;
+                next = m;
+            }
+            Msh[0 * nc + c] = 2.0 * Msh[1 * nc + c] - Msh[2 * nc + c];
+            Msh[(T - 1) * nc + c] = 2.0 * Msh[(T - 2) * nc + c] - Msh[(T - 3) * nc + c];
+        }
+        __syncthreads();
+
+        // (3) evaluate k*T frames in float64, cast to float32 (torch.Tensor(...) in the notebook)
+        const int rows_per_step = (int)blockDim.x / ncl;
+        const int cl = tid % ncl, col = col0 + cl;
+        const int v = col / p.C, c = col - v * p.C;
+        float* op = p.planar ? p.out + ((n * p.C + c) * KT) * p.V + v            // (N, C, k*T, V)
+                             : p.out + n * KT * VC + col;                         // (N, k*T, V, C)
+        const long long ostride = p.planar ? p.V : VC;
+        int jc = -1;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        for (long long i = tid / ncl; i < KT && tid < rows_per_step * ncl; i += rows_per_step) {
+            int j;
+            double tt;
+            pf_locate(i, p.ratio, T, j, tt);
+            if (j != jc) {
+                pf_cubic(ys[j * nc + cl], ys[(j + 1) * nc + cl], Msh[j * nc + cl], Msh[(j + 1) * nc + cl], a0, a1, a2, a3);
+                jc = j;
+            }
+            op[i * ostride] = pf_eval(tt, a0, a1, a2, a3);
+        }
+    }
+}
+#endif  // __CUDACC__
+
 }  // namespace vr

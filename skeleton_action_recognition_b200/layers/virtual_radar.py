@@ -265,8 +265,13 @@ class VirtualRadar(torch.nn.Module):
 
     def forward(self, x):
         self._check_input(x)
-        lam, loc = self._check_device(x)
+        self._check_device(x)
         xc, flags = self._prepare(x)
+        return self._run(x, xc, flags)
+
+    def _run(self, x, xc, flags):
+        """forward() after the layout has been normalised: xc standard-contiguous, flags carry the range rounding mode."""
+        lam, loc = self.wavelength, self.radar_location
         if self._general_stft():     # trained / trainable STFT kernels: synthesis on our kernels, STFT as a GEMM
             if xc.shape[2] <= max(self.n_fft, self._FUSED_N_FFT) // 2:
                 raise ValueError("T=%d must exceed n_fft/2=%d: reflect padding needs it"
@@ -278,6 +283,22 @@ class VirtualRadar(torch.nn.Module):
         if self._needs_grad(x) and xc.shape[0] > 0:
             return _RadarFunction.apply(lam, loc, xc, self, flags)
         return self._launch(xc, flags)[0]
+
+    def forward_notebook(self, data, num_pad_frames=1, sigma=3):
+        """virtual_radar_example.ipynb cells 2-4 on the device: `data` is one body's (T, V, 3) array (or a batch
+        (N, T, V, 3)), float64 or float32 CUDA tensor.  Equals
+        `self(torch.Tensor(np.expand_dims(utils.pad_frames(data, num_pad_frames, sigma).transpose(2, 0, 1), [0, -1])))`
+        of the reference (utils.py:82-89 + layers/virtual_radar.py:79-134): the up-sampling kernel writes float32 straight
+        in the layer's layout (C ABI vr_pad_frames_joints, planar), and the launch is told to round the radar range the way
+        the reference does for the notebook's coordinate-innermost tensor (VR_FLAG_RANGE_FMA) -- no layout copy of the
+        k-times larger array in between."""
+        from ..upsample import pad_frames_notebook
+        if isinstance(data, torch.Tensor) and data.shape[-1] != 3:
+            raise ValueError("expected (T, V, 3) or (N, T, V, 3) joint positions, got %s" % (tuple(data.shape),))
+        x = pad_frames_notebook(data, num_pad_frames, sigma, planar=True)
+        self._check_input(x)
+        self._check_device(x)
+        return self._run(x, x, _cabi.VR_FLAG_RANGE_FMA)
 
     def forward_image(self, x, image_size=256):
         """The layer fused with its consumer's input stage (reference models/resnet.py:24-26):

@@ -85,5 +85,16 @@ def full_case(name):
     x = notebook_tensor(pad_frames(raw * c["scale"] if c["scale"] != 1.0 else raw, num_pad_frames=c["pad"]))
     g = load("full_outputs.npz")
     gold = {"y": g[name + "_y"], "iq": g[name + "_iq"], "rowsum": g[name + "_rowsum"], "stride": int(g["stride"]),
-            "x_strides": tuple(int(s) for s in g[name + "_x_strides"])}
+            "x_strides": tuple(int(s) for s in g[name + "_x_strides"]),
+            "up": g[name + "_up"], "up_sum": float(g[name + "_up_sum"])}
     return x, c["kw"], gold
+
+
+def full_raw(name):
+    """The raw (T, V, 3) array of a full-size case as the notebook holds it before `pad_frames` (dtype as in the
+    reference's files: NTU float32, CMU / gait float64; CMU scaled to metres), and the up-sampling factor."""
+    c = FULL[name]
+    raw = load("full_inputs.npz")[name]
+    if name == "cmu":
+        raw = raw.astype(np.float64) * c["scale"]
+    return raw, c["pad"]

@@ -10,7 +10,8 @@ Writes
                     81 920 and the C-innermost strides are the notebook's.
   full_outputs.npz  from the real reference's forward (layers/virtual_radar.py loaded by path, nnAudio restated):
                     every STRIDE-th spectrogram column and every 16th baseband sample of each run (the full
-                    outputs are 3.5-10.5 MB each), plus a float64 checksum per spectrogram row over ALL columns.
+                    outputs are 3.5-10.5 MB each), plus a float64 checksum per spectrogram row over ALL columns; and from
+                    the real utils.pad_frames (utils.py:82-89): every 997th up-sampled frame (float32) and the sum.
 known_answers.json (rows B, C, D: shape / sum / min / max / argmax) comes from make_golden.py.
 """
 import os
@@ -25,6 +26,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, HERE)
 
 from make_golden import load_reference, ref_iq, GAIT_EDGES, REF  # noqa: E402
+from make_golden_pad_frames import load_reference_utils  # noqa: E402
 from oracle.pad_frames import pad_frames, notebook_tensor  # noqa: E402
 
 STRIDE = 48
@@ -46,8 +48,13 @@ def main():
         "gait": (gait, 10, dict(edges=GAIT_EDGES, wavelength=5e-4)),                              # cell 3 -> row D
     }
     out = {"stride": STRIDE}
+    ref_utils = load_reference_utils()                       # the REAL utils.py (pad_frames, utils.py:82-89)
     for name, (raw, pad, kw) in cases.items():
-        x = notebook_tensor(pad_frames(raw, num_pad_frames=pad))
+        up = ref_utils.pad_frames(raw, num_pad_frames=pad)
+        assert np.array_equal(up, pad_frames(raw, num_pad_frames=pad))      # the oracle's restatement is the same function
+        out[name + "_up"] = np.ascontiguousarray(up[::997].astype(np.float32))   # every 997th up-sampled frame, as torch.Tensor casts it
+        out[name + "_up_sum"] = np.float64(up.astype(np.float32).astype(np.float64).sum())
+        x = notebook_tensor(up)
         layer = ref.VirtualRadar(device="cpu", **kw)
         y, iq = ref_iq(layer, x)
         y, iq = y.numpy(), iq.numpy()

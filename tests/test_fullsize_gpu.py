@@ -84,6 +84,74 @@ def test_notebook_configs_at_full_size(name):
         assert theta_max > 1.4e5                                      # beyond anything the crops exercise (44 k rad)
 
 
+@pytest.mark.parametrize("name", sorted(fx.FULL))
+def test_notebook_pad_frames_on_the_device(name):
+    """`utils.pad_frames` (reference utils.py:82-89: Gaussian along the JOINT axis, cubic in time, float64) on the GPU
+    (C ABI vr_pad_frames_joints) at the notebook's full sizes: float32 positions equal to the real reference's (golden
+    samples made with the real utils.py) and to scipy run here, in both output layouts; and the two-launch device
+    pipeline `forward_notebook` gives the very spectrogram of the host-prepared notebook tensor."""
+    from skeleton_action_recognition_b200 import pad_frames_notebook
+    raw, k = fx.full_raw(name)
+    x_host, kw, gold = fx.full_case(name)                     # scipy on the host + the notebook's transposes
+    dev_raw = torch.from_numpy(raw).cuda()
+    up = pad_frames_notebook(dev_raw, k)                      # (1, 3, kT, V, 1), the notebook's strides
+    assert tuple(up.shape) == tuple(x_host.shape) and up.stride()[1:4] == x_host.stride()[1:4] and up.stride(1) == 1
+    got = up.cpu()
+    rows = got[0, :, :, :, 0].permute(1, 2, 0).numpy()        # (kT, V, 3)
+    assert np.array_equal(rows[::997], gold["up"])            # the real utils.pad_frames, cast like torch.Tensor(...)
+    # every position against scipy on this host.  Equal except at zero crossings of a coordinate: there the cubic's terms
+    # cancel, |value| is 1e-8 .. 1e-37 of the coefficients, and the two float64 evaluations (scipy's B-spline recursion,
+    # the kernel's Horner form) differ by enough to land on the two sides of a float32 rounding boundary -- 1 of 4.2 M
+    # positions for the gait file, 4 of 12.4 M for NTU, none for CMU (tools/pad_nb_diag.py prints them).  One float32 ulp
+    # of a 1e-8 m coordinate is 1e-15 m: it cannot move a range.
+    a, b = got.numpy(), x_host.numpy()
+    bad = a != b
+    assert bad.sum() <= 1e-6 * a.size, int(bad.sum())
+    if bad.any():
+        scale = np.abs(b).max()
+        assert np.abs(b[bad]).max() < 1e-6 * scale, (np.abs(b[bad]).max(), scale)
+        ulp = np.abs(a[bad].view(np.int32).astype(np.int64) - b[bad].view(np.int32).astype(np.int64))
+        assert ulp.max() == 1, ulp
+    assert abs(float(got.double().sum()) - gold["up_sum"]) < 1e-9 * max(1.0, abs(gold["up_sum"]))
+    planar = pad_frames_notebook(dev_raw, k, planar=True)
+    assert planar.is_contiguous() and torch.equal(planar, up.contiguous())
+    layer = _layer(**kw)
+    want = layer(x_host.cuda())                               # the host-prepared notebook tensor
+    dev = layer(up)                                           # same strides -> same range rounding mode
+    assert torch.equal(layer.forward_notebook(dev_raw, k), dev)       # planar layout + explicit mode: the same bits
+    assert not torch.equal(layer(planar), dev)                # the planar copy alone would select the other mode
+    if not bad.any():
+        assert torch.equal(dev, want)
+    assert vro.parity_ok(vro.parity_report(dev.cpu().numpy(), want.cpu().numpy()))
+    s = gold["stride"]
+    assert vro.parity_ok(vro.parity_report(dev.cpu().numpy()[:, :, ::s], gold["y"]))
+    _record("notebook_pad/" + name, {"positions_differing_from_scipy": int(bad.sum()), "positions": int(a.size),
+                                     "spectrogram_bit_equal_to_host_prepared": bool(torch.equal(dev, want))})
+
+
+def test_notebook_pad_frames_shapes_and_errors():
+    from skeleton_action_recognition_b200 import pad_frames_notebook
+    from oracle.pad_frames import pad_frames as host_pad
+    g = torch.Generator().manual_seed(31)
+    for shape, k, sigma, dt in (((40, 5, 3), 7, 3, torch.float64), ((4, 3, 3), 3, 1, torch.float32), ((500, 42, 3), 5, 2, torch.float64),
+                                ((64, 25, 2), 9, 3, torch.float32)):
+        a = torch.randn(*shape, generator=g, dtype=dt)
+        want = torch.Tensor(host_pad(a.numpy(), k, sigma))                       # (kT, V, C) float32
+        got = pad_frames_notebook(a.cuda(), k, sigma)
+        assert tuple(got.shape) == (1, shape[2], k * shape[0], shape[1], 1)
+        assert torch.equal(got[0, :, :, :, 0].permute(1, 2, 0).cpu(), want), (shape, k)
+    batch = torch.randn(3, 50, 6, 3, generator=g, dtype=torch.float64)
+    got = pad_frames_notebook(batch.cuda(), 4)
+    for n in range(3):
+        assert torch.equal(got[n:n + 1], pad_frames_notebook(batch[n].cuda(), 4))
+    with pytest.raises(ValueError):
+        pad_frames_notebook(torch.zeros(3, 5, 3, device="cuda"), 4)              # T < 4
+    with pytest.raises(NotImplementedError):
+        pad_frames_notebook(torch.zeros(9000, 2, 3, device="cuda", dtype=torch.float64), 2)
+    with pytest.raises(RuntimeError):
+        pad_frames_notebook(torch.zeros(10, 5, 3), 4)
+
+
 @pytest.mark.parametrize("offset,lam", [((0., 0., 5.), 5e-4), ((6., -3., 7.), 5e-4), ((2., 9., -4.), 9e-4)])
 def test_far_targets_large_phase(offset, lam):
     """randn bodies 5-10 m from the radar: theta = 4 pi d / lambda reaches 1.2e5 .. 2.6e5 rad, where one ulp of theta
