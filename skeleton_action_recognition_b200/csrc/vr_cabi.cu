@@ -5,6 +5,7 @@
 #include "vr_kernels.cuh"
 #include "vr_pad_frames.cuh"
 #include "vr_backward.cuh"
+#include "vr_stft_gemm.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -910,6 +911,113 @@ int vr_partition_edges(const int32_t* src_host, const int32_t* dst_host, int32_t
     int rc = partition_edges(src_host, dst_host, E, V, P);
     if (rc) return rc;
     for (int e = 0; e < E; ++e) group_of_edge[e] = P.group_of_edge[e];
+    return VR_OK;
+}
+
+}  // extern "C"
+
+// ---- the STFT against general kernels: tcgen05 GEMM (vr_stft_gemm.cuh) --------------------------------------------
+namespace {
+int gemm_setup(int dev) {
+    static std::mutex mu;
+    static bool done[64] = {false};
+    std::lock_guard<std::mutex> lk(mu);
+    if (!done[dev]) {
+        CUDA_TRY(cudaFuncSetAttribute(vr::vr_gemm_tf32x3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, vr::G_SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(vr::vr_gemm_tf32x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, vr::G_SMEM_BYTES));
+        done[dev] = true;
+    }
+    return VR_OK;
+}
+int stft_nb(int n_fft) { return n_fft < vr::GN / 2 ? n_fft : vr::GN / 2; }    // bins per column tile: [re block | im block]
+int stft_check(int64_t N, int64_t T, int n_fft, int hop) {
+    if (N <= 0 || T <= 0 || hop <= 0) return fail(VR_ERR_SHAPE, "N, T, hop must be positive");
+    if (n_fft < 16 || n_fft > 1024 || (n_fft & (n_fft - 1)) != 0) return fail(VR_ERR_UNSUPPORTED, "n_fft must be a power of two in [16, 1024], got %d", n_fft);
+    if (T <= n_fft / 2) return fail(VR_ERR_SHAPE, "T=%lld must exceed n_fft/2=%d: reflect padding needs it", (long long)T, n_fft / 2);
+    if (N * (T / hop + 1) >= (1ll << 31) / 2) return fail(VR_ERR_UNSUPPORTED, "too many frames for one launch; split the batch");
+    return VR_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int64_t vr_stft_general_workspace_floats(int64_t N, int64_t T, int32_t n_fft, int32_t hop, int64_t parts[3]) {
+    if (N <= 0 || T <= 0 || hop <= 0 || n_fft <= 0) return 0;
+    const int64_t M = N * (T / hop + 1), K = 2ll * n_fft;
+    const int64_t a = M * K, b = K * K, c = M * K;
+    if (parts) { parts[0] = a; parts[1] = b; parts[2] = c; }
+    return a + b + c;
+}
+
+int vr_stft_general_f32(const float* iq_dev, int64_t N, int64_t T, int32_t n_fft, int32_t hop,
+                        const float* wsin_dev, const float* wcos_dev, float* frames_work, float* bt_work,
+                        float* c_save /* may be NULL */, float* out_dev, void* stream) {
+    if (!iq_dev || !wsin_dev || !wcos_dev || !frames_work || !bt_work || !out_dev) return fail(VR_ERR_ARG, "device pointers must not be null");
+    int rc = stft_check(N, T, n_fft, hop);
+    if (rc) return rc;
+    int dev, sm_count;
+    rc = device_setup(dev, sm_count);
+    if (rc) return rc;
+    rc = gemm_setup(dev);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int F = (int)(T / hop) + 1, nb = stft_nb(n_fft), K = 2 * n_fft;
+    const long long M = N * (long long)F;
+    vr::vr_stft_frames_kernel<<<(unsigned)std::min<long long>((M * n_fft + 255) / 256, sm_count * 16ll), 256, 0, st>>>(iq_dev, frames_work, N, (int)T, F, n_fft, hop);
+    vr::vr_stft_bt_kernel<<<(n_fft * n_fft + 255) / 256, 256, 0, st>>>(wsin_dev, wcos_dev, bt_work, n_fft, nb);
+    vr::GemmParams g;
+    memset(&g, 0, sizeof(g));
+    g.A = frames_work; g.sAm = K; g.sAk = 1;
+    g.B = bt_work; g.sBn = K; g.sBk = 1;
+    g.M = (int)M; g.N = K; g.K = K;
+    g.out = out_dev; g.csave = c_save; g.F = F; g.n_fft = n_fft; g.nb = nb;
+    dim3 grid((unsigned)((M + vr::GM - 1) / vr::GM), (unsigned)((K + vr::GN - 1) / vr::GN));
+    vr::vr_gemm_tf32x3_kernel<1><<<grid, 128, vr::G_SMEM_BYTES, st>>>(g);
+    CUDA_TRY(cudaGetLastError());
+    return VR_OK;
+}
+
+int vr_stft_general_backward_f32(const float* grad_out_dev, const float* frames_work, const float* bt_work, const float* c_save,
+                                 int64_t N, int64_t T, int32_t n_fft, int32_t hop,
+                                 float* dc_work, float* da_work /* NULL: no grad_iq */, float* dbt_work /* NULL: no kernel grads */,
+                                 float* grad_iq_dev, float* grad_wsin_dev, float* grad_wcos_dev, void* stream) {
+    if (!grad_out_dev || !frames_work || !bt_work || !c_save || !dc_work) return fail(VR_ERR_ARG, "device pointers must not be null");
+    if ((da_work == nullptr) != (grad_iq_dev == nullptr)) return fail(VR_ERR_ARG, "da_work and grad_iq_dev go together");
+    if ((dbt_work == nullptr) != (grad_wsin_dev == nullptr) || (dbt_work == nullptr) != (grad_wcos_dev == nullptr))
+        return fail(VR_ERR_ARG, "dbt_work, grad_wsin_dev and grad_wcos_dev go together");
+    int rc = stft_check(N, T, n_fft, hop);
+    if (rc) return rc;
+    int dev, sm_count;
+    rc = device_setup(dev, sm_count);
+    if (rc) return rc;
+    rc = gemm_setup(dev);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int F = (int)(T / hop) + 1, nb = stft_nb(n_fft), K = 2 * n_fft;
+    const long long M = N * (long long)F;
+    const unsigned eb = (unsigned)std::min<long long>((M * n_fft + 255) / 256, sm_count * 16ll);
+    vr::vr_stft_dc_kernel<<<eb, 256, 0, st>>>(grad_out_dev, c_save, dc_work, M, F, n_fft, nb);
+    vr::GemmParams g;
+    if (da_work) {                                   // dA[m, k] = sum_n dC[m, n] Bt[n, k]
+        memset(&g, 0, sizeof(g));
+        g.A = dc_work; g.sAm = K; g.sAk = 1;
+        g.B = bt_work; g.sBn = 1; g.sBk = K;         // B'(n' = k, k' = n) = Bt[n][k]
+        g.M = (int)M; g.N = K; g.K = K; g.C = da_work; g.ldc = K;
+        dim3 grid((unsigned)((M + vr::GM - 1) / vr::GM), (unsigned)((K + vr::GN - 1) / vr::GN));
+        vr::vr_gemm_tf32x3_kernel<0><<<grid, 128, vr::G_SMEM_BYTES, st>>>(g);
+        CUDA_TRY(cudaMemsetAsync(grad_iq_dev, 0, (size_t)N * T * 2 * sizeof(float), st));
+        vr::vr_stft_fold_kernel<<<eb, 256, 0, st>>>(da_work, grad_iq_dev, N, (int)T, F, n_fft, hop);
+    }
+    if (dbt_work) {                                  // dBt[n, k] = sum_m dC[m, n] A[m, k]
+        memset(&g, 0, sizeof(g));
+        g.A = dc_work; g.sAm = 1; g.sAk = K;         // A'(m' = n, k' = m) = dC[m][n]
+        g.B = frames_work; g.sBn = 1; g.sBk = K;     // B'(n' = k, k' = m) = A[m][k]
+        g.M = K; g.N = K; g.K = (int)M; g.C = dbt_work; g.ldc = K;
+        dim3 grid((unsigned)((K + vr::GM - 1) / vr::GM), (unsigned)((K + vr::GN - 1) / vr::GN));
+        vr::vr_gemm_tf32x3_kernel<0><<<grid, 128, vr::G_SMEM_BYTES, st>>>(g);
+        vr::vr_stft_dw_kernel<<<(n_fft * n_fft + 255) / 256, 256, 0, st>>>(dbt_work, grad_wsin_dev, grad_wcos_dev, n_fft, nb);
+    }
+    CUDA_TRY(cudaGetLastError());
     return VR_OK;
 }
 

@@ -64,10 +64,17 @@ class _STFTKernels(torch.nn.Module):
             raise NotImplementedError("stft.wsin/wcos differ from the Hann-windowed Fourier kernels")
 
     def logmag(self, iq):
-        """General-kernel path (trained or trainable `wsin`/`wcos`): what the reference computes at
-        layers/virtual_radar.py:124-133 with nnAudio's conv1d STFT, as one float32 GEMM per kernel on the
-        reflect-padded, framed baseband signal (cuBLAS through torch.matmul; differentiable with respect to
-        `wsin`, `wcos` and `iq`).  iq (N,T,2) -> (N, n_fft, T//hop+1)."""
+        """General-kernel path (trained or trainable `wsin`/`wcos`, or an `n_fft` the fused FFT does not cover): what the
+        reference computes at layers/virtual_radar.py:124-133 with nnAudio's conv1d STFT, as one float32-accurate GEMM per
+        batch on the tensor cores (C ABI vr_stft_general_f32: tcgen05.mma kind::tf32, 3-term split, accumulator in tensor
+        memory, magnitude / log / roll in the epilogue), differentiable with respect to `wsin`, `wcos` and `iq`
+        (vr_stft_general_backward_f32).  iq (N,T,2) CUDA float32 -> (N, n_fft, T//hop+1)."""
+        if not iq.is_cuda:
+            raise RuntimeError("the general-kernel STFT (B200) has no CPU path")
+        return _GeneralSTFTFunction.apply(iq, self.wsin, self.wcos, self.n_fft, self.stride)
+
+    def _logmag_torch(self, iq):
+        """TEST CROSS-CHECK ONLY (never called by forward): the same computation with torch ops (cuBLAS GEMM + autograd)."""
         n = self.n_fft
         zp = torch.nn.functional.pad(iq.permute(0, 2, 1), (n // 2, n // 2), mode="reflect")       # (N,2,T+n)
         frames = zp.unfold(2, n, self.stride)                                                       # (N,2,F,n)
@@ -78,6 +85,61 @@ class _STFTKernels(torch.nn.Module):
         mag = torch.sqrt(real * real + imag * imag)
         out = torch.log(mag + 1e-6).transpose(1, 2)                                                 # (N,n_fft,F)
         return torch.roll(out, n // 2, dims=1)
+
+
+class _GeneralSTFTFunction(torch.autograd.Function):
+    """STFT against general kernels + log-magnitude + roll: forward and backward are the tcgen05 GEMM kernels of
+    csrc/vr_stft_gemm.cuh behind vr_stft_general_f32 / vr_stft_general_backward_f32 (no library GEMM, no autograd graph)."""
+
+    @staticmethod
+    def forward(ctx, iq, wsin, wcos, n_fft, hop):
+        iq = iq.contiguous()
+        if iq.dtype != torch.float32 or wsin.dtype != torch.float32:
+            raise ValueError("the general-kernel STFT computes in float32")
+        N, T, _ = iq.shape
+        L = _cabi.lib()
+        parts = (ctypes.c_int64 * 3)()
+        L.vr_stft_general_workspace_floats(N, T, n_fft, hop, parts)
+        dev = iq.device
+        frames = torch.empty(max(int(parts[0]), 1), dtype=torch.float32, device=dev)
+        bt = torch.empty(max(int(parts[1]), 1), dtype=torch.float32, device=dev)
+        need = any(ctx.needs_input_grad[:3])
+        csave = torch.empty(max(int(parts[2]), 1), dtype=torch.float32, device=dev) if need else None
+        out = torch.empty((N, n_fft, T // hop + 1), dtype=torch.float32, device=dev)
+        if N > 0:
+            with torch.cuda.device(dev):
+                stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+                rc = L.vr_stft_general_f32(iq.data_ptr(), N, T, n_fft, hop, wsin.contiguous().data_ptr(), wcos.contiguous().data_ptr(),
+                                           frames.data_ptr(), bt.data_ptr(), csave.data_ptr() if need else None,
+                                           out.data_ptr(), stream)
+            _cabi.check(rc)
+        if need:
+            ctx.save_for_backward(frames, bt, csave)
+        ctx.dims = (N, T, n_fft, hop, tuple(wsin.shape))
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        frames, bt, csave = ctx.saved_tensors
+        N, T, n_fft, hop, wshape = ctx.dims
+        dev = gout.device
+        need_iq, need_w = ctx.needs_input_grad[0], (ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
+        g = gout.contiguous().to(torch.float32)
+        dc = torch.empty_like(csave)
+        da = torch.empty_like(frames) if need_iq else None
+        dbt = torch.empty_like(bt) if need_w else None
+        giq = torch.empty((N, T, 2), dtype=torch.float32, device=dev) if need_iq else None
+        gsin = torch.empty(wshape, dtype=torch.float32, device=dev) if need_w else None
+        gcos = torch.empty(wshape, dtype=torch.float32, device=dev) if need_w else None
+        if N > 0:
+            ptr = lambda t: t.data_ptr() if t is not None else None     # noqa: E731
+            with torch.cuda.device(dev):
+                stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+                rc = _cabi.lib().vr_stft_general_backward_f32(g.data_ptr(), frames.data_ptr(), bt.data_ptr(), csave.data_ptr(),
+                                                              N, T, n_fft, hop, dc.data_ptr(), ptr(da), ptr(dbt),
+                                                              ptr(giq), ptr(gsin), ptr(gcos), stream)
+            _cabi.check(rc)
+        return (giq, gsin if ctx.needs_input_grad[1] else None, gcos if ctx.needs_input_grad[2] else None, None, None)
 
 
 class _RadarFunction(torch.autograd.Function):

@@ -1,0 +1,120 @@
+"""GPU tests of the general-kernel STFT (csrc/vr_stft_gemm.cuh behind vr_stft_general_f32 / vr_stft_general_backward_f32:
+tcgen05.mma kind::tf32 with the 3-term split, accumulator in tensor memory): forward against the oracle's conv1d
+restatement of nnAudio (oracle/nnaudio_stft.py) within the layer's tiered criterion, for analytic and for perturbed
+("trained") kernels and n_fft in {64, 128, 256, 512}; gradients against float64 autograd of the same graph; and the torch
+restatement (cuBLAS GEMM) as a cross-check and timing reference."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import virtual_radar_oracle as vro
+from oracle.nnaudio_stft import STFT
+from tests import fixtures as fx
+
+pytestmark = pytest.mark.gpu
+
+
+def _kernels(n_fft, hop, perturb, seed=0):
+    from skeleton_action_recognition_b200.layers.virtual_radar import _STFTKernels
+    k = _STFTKernels(n_fft, hop, True, "cuda:0")
+    if perturb:
+        g = torch.Generator().manual_seed(seed)
+        with torch.no_grad():
+            k.wsin.add_((perturb * torch.randn(k.wsin.shape, generator=g)).cuda())
+            k.wcos.add_((perturb * torch.randn(k.wcos.shape, generator=g)).cuda())
+    return k
+
+
+def _oracle(iq, k, n_fft, hop):
+    st = STFT(n_fft=n_fft, freq_bins=n_fft, hop_length=hop, output_format="Complex", device="cpu")
+    st.wsin.data, st.wcos.data = k.wsin.detach().cpu(), k.wcos.detach().cpu()
+    return vro.stft_logmag(iq, st, n_fft).detach().numpy()
+
+
+@pytest.mark.parametrize("n_fft,hop,T,N,perturb", [(256, 16, 300, 5, 0.0), (256, 16, 300, 40, 0.02), (128, 16, 600, 3, 0.02),
+                                                   (512, 32, 700, 3, 0.01), (64, 8, 333, 4, 0.05), (256, 16, 5000, 2, 0.02),
+                                                   (256, 100, 1001, 3, 0.0)])
+def test_forward_matches_the_conv1d_restatement(n_fft, hop, T, N, perturb):
+    g = torch.Generator().manual_seed(n_fft + T)
+    t = torch.arange(T, dtype=torch.float32)[None, :, None]
+    # a realistic baseband signal: a few strong tones (60 dB of dynamic range) plus noise
+    ph = torch.rand(N, 1, 1, generator=g) * 6.28
+    iq = (3.0 * torch.stack((torch.cos(0.3 * t + ph), torch.sin(0.3 * t + ph)), -1).squeeze(2)
+          + 0.5 * torch.stack((torch.cos(-1.1 * t), torch.sin(-1.1 * t)), -1).squeeze(2)
+          + 0.01 * torch.randn(N, T, 2, generator=g))
+    k = _kernels(n_fft, hop, perturb)
+    with torch.no_grad():
+        got = k.logmag(iq.cuda())
+        lib = k._logmag_torch(iq.cuda())
+    assert tuple(got.shape) == (N, n_fft, T // hop + 1)
+    ref = _oracle(iq, k, n_fft, hop)
+    rep = vro.parity_report(got.cpu().numpy(), ref)
+    assert vro.parity_ok(rep), rep
+    # and no further from the oracle than the library GEMM it replaces
+    rep_lib = vro.parity_report(lib.cpu().numpy(), ref)
+    assert rep["global_abs_over_peak"] <= max(2 * rep_lib["global_abs_over_peak"], 2e-6), (rep["global_abs_over_peak"], rep_lib["global_abs_over_peak"])
+
+
+@pytest.mark.parametrize("n_fft,hop,T,N", [(256, 16, 300, 6), (128, 16, 400, 3), (64, 8, 200, 2)])
+def test_backward_matches_float64_autograd(n_fft, hop, T, N):
+    g = torch.Generator().manual_seed(n_fft)
+    iq = torch.randn(N, T, 2, generator=g)
+    go = torch.randn(N, n_fft, T // hop + 1, generator=g)
+    k = _kernels(n_fft, hop, 0.02, seed=3)
+    x = iq.cuda().requires_grad_(True)
+    (k.logmag(x) * go.cuda()).sum().backward()
+    got = (x.grad.cpu().double(), k.wsin.grad.cpu().double(), k.wcos.grad.cpu().double())
+    # float64 truth of the same graph (torch ops on the CPU)
+    k64 = _kernels(n_fft, hop, 0.0)
+    k64 = k64.double().cpu()
+    with torch.no_grad():
+        k64.wsin.copy_(k.wsin.detach().cpu().double())
+        k64.wcos.copy_(k.wcos.detach().cpu().double())
+    x64 = iq.double().requires_grad_(True)
+    (k64._logmag_torch(x64) * go.double()).sum().backward()
+    want = (x64.grad, k64.wsin.grad, k64.wcos.grad)
+    # the yardstick: float32 autograd over the torch restatement (cuBLAS GEMM) of the same graph on the GPU.  Bins whose
+    # magnitude is nearly zero make d ln|X| = Re(conj(X) dX) / |X|^2 ill-conditioned in float32 for ANY implementation,
+    # so the bar is "as close to the float64 truth as the library path", not an absolute number.
+    kl = _kernels(n_fft, hop, 0.0)
+    with torch.no_grad():
+        kl.wsin.copy_(k.wsin)
+        kl.wcos.copy_(k.wcos)
+    xl = iq.cuda().requires_grad_(True)
+    (kl._logmag_torch(xl) * go.cuda()).sum().backward()
+    lib = (xl.grad.cpu().double(), kl.wsin.grad.cpu().double(), kl.wcos.grad.cpu().double())
+    for name, a, b, c in zip(("iq", "wsin", "wcos"), got, want, lib):
+        scale = b.square().mean().sqrt()
+        err, err_lib = (a - b).abs().max() / scale, (c - b).abs().max() / scale
+        med, med_lib = (a - b).abs().median() / scale, (c - b).abs().median() / scale
+        print("%s: tcgen05 max %.2e median %.2e | library f32 max %.2e median %.2e" % (name, err, med, err_lib, med_lib))
+        assert err < max(3 * err_lib, 2e-4) and med < max(3 * med_lib, 2e-6), (name, float(err), float(err_lib), float(med), float(med_lib))
+    # frozen kernels: only dL/d(iq); frozen signal: only the kernel gradients
+    k.zero_grad()
+    kf = _kernels(n_fft, hop, 0.0)
+    kf.wsin.requires_grad_(False)
+    kf.wcos.requires_grad_(False)
+    x2 = iq.cuda().requires_grad_(True)
+    kf.logmag(x2).sum().backward()
+    assert x2.grad is not None and kf.wsin.grad is None
+    k.logmag(iq.cuda()).sum().backward()
+    assert k.wsin.grad is not None
+
+
+def test_layer_with_trained_kernels_end_to_end():
+    """Through the module: synthesis kernel -> tcgen05 STFT, forward parity against the oracle with the same trained kernels
+    and gradients flowing to the kernels, the wavelength and x."""
+    x = fx.s3_smooth(4, T=300)
+    from skeleton_action_recognition_b200 import VirtualRadar
+    layer = VirtualRadar(wavelength=5e-3, train_stft_kernel=True, train_wavelength=True, device="cuda:0").to("cuda:0")
+    g = torch.Generator().manual_seed(5)
+    with torch.no_grad():
+        layer.stft.wsin.add_((0.02 * torch.randn(layer.stft.wsin.shape, generator=g)).cuda())
+    xg = x.cuda().requires_grad_(True)
+    out = layer(xg)
+    o = vro.OracleVirtualRadar(wavelength=5e-3)
+    o.stft.wsin.data, o.stft.wcos.data = layer.stft.wsin.detach().cpu(), layer.stft.wcos.detach().cpu()
+    rep = vro.parity_report(out.detach().cpu().numpy(), o(x, "seq").numpy())
+    assert vro.parity_ok(rep), rep
+    out.square().mean().backward()
+    assert torch.isfinite(layer.wavelength.grad) and layer.stft.wsin.grad.abs().sum() > 0 and xg.grad.abs().sum() > 0
