@@ -969,7 +969,7 @@ int vr_stft_general_f32(const float* iq_dev, int64_t N, int64_t T, int32_t n_fft
     memset(&g, 0, sizeof(g));
     g.A = frames_work; g.sAm = K; g.sAk = 1;
     g.B = bt_work; g.sBn = K; g.sBk = 1;
-    g.M = (int)M; g.N = K; g.K = K;
+    g.M = (int)M; g.N = K; g.K = K; g.kb_per_split = (K + vr::GK - 1) / vr::GK;
     g.out = out_dev; g.csave = c_save; g.F = F; g.n_fft = n_fft; g.nb = nb;
     dim3 grid((unsigned)((M + vr::GM - 1) / vr::GM), (unsigned)((K + vr::GN - 1) / vr::GN));
     vr::vr_gemm_tf32x3_kernel<1><<<grid, 128, vr::G_SMEM_BYTES, st>>>(g);
@@ -1002,7 +1002,7 @@ int vr_stft_general_backward_f32(const float* grad_out_dev, const float* frames_
         memset(&g, 0, sizeof(g));
         g.A = dc_work; g.sAm = K; g.sAk = 1;
         g.B = bt_work; g.sBn = 1; g.sBk = K;         // B'(n' = k, k' = n) = Bt[n][k]
-        g.M = (int)M; g.N = K; g.K = K; g.C = da_work; g.ldc = K;
+        g.M = (int)M; g.N = K; g.K = K; g.C = da_work; g.ldc = K; g.kb_per_split = (K + vr::GK - 1) / vr::GK;
         dim3 grid((unsigned)((M + vr::GM - 1) / vr::GM), (unsigned)((K + vr::GN - 1) / vr::GN));
         vr::vr_gemm_tf32x3_kernel<0><<<grid, 128, vr::G_SMEM_BYTES, st>>>(g);
         CUDA_TRY(cudaMemsetAsync(grad_iq_dev, 0, (size_t)N * T * 2 * sizeof(float), st));
@@ -1013,7 +1013,15 @@ int vr_stft_general_backward_f32(const float* grad_out_dev, const float* frames_
         g.A = dc_work; g.sAm = 1; g.sAk = K;         // A'(m' = n, k' = m) = dC[m][n]
         g.B = frames_work; g.sBn = 1; g.sBk = K;     // B'(n' = k, k' = m) = A[m][k]
         g.M = K; g.N = K; g.K = (int)M; g.C = dbt_work; g.ldc = K;
-        dim3 grid((unsigned)((K + vr::GM - 1) / vr::GM), (unsigned)((K + vr::GN - 1) / vr::GN));
+        // the reduction runs over all frames of the batch: split it over gridDim.z so that the (2 n_fft / 128)^2 output
+        // tiles fill the machine; the slices add into the zeroed result with float atomics
+        const int tiles = ((K + vr::GM - 1) / vr::GM) * ((K + vr::GN - 1) / vr::GN);
+        const int kb_all = (int)((M + vr::GK - 1) / vr::GK);
+        int splits = std::max(1, std::min((2 * sm_count + tiles - 1) / tiles, (kb_all + 7) / 8));
+        g.kb_per_split = (kb_all + splits - 1) / splits;
+        splits = (kb_all + g.kb_per_split - 1) / g.kb_per_split;
+        if (splits > 1) CUDA_TRY(cudaMemsetAsync(dbt_work, 0, (size_t)K * K * sizeof(float), st));
+        dim3 grid((unsigned)((K + vr::GM - 1) / vr::GM), (unsigned)((K + vr::GN - 1) / vr::GN), (unsigned)splits);
         vr::vr_gemm_tf32x3_kernel<0><<<grid, 128, vr::G_SMEM_BYTES, st>>>(g);
         vr::vr_stft_dw_kernel<<<(n_fft * n_fft + 255) / 256, 256, 0, st>>>(dbt_work, grad_wsin_dev, grad_wcos_dev, n_fft, nb);
     }

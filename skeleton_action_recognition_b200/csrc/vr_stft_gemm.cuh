@@ -40,6 +40,7 @@ struct GemmParams {
     const float* A; long long sAm, sAk;             // A(m, k) = A[m * sAm + k * sAk]
     const float* B; long long sBn, sBk;             // B(n, k) = B[n * sBn + k * sBk]    (C = A . B^T)
     int M, N, K;
+    int kb_per_split;                               // K blocks per gridDim.z slice (EPI 0 accumulates with atomics when gridDim.z > 1)
     float* C; long long ldc;                        // EPI 0: C[m * ldc + n]
     float* out; float* csave;                       // EPI 1: (sequences, n_fft, F) log-magnitude; optional raw C (M x N)
     int F, n_fft, nb;                               // frames per sequence; bins per column tile (re block | im block)
@@ -102,7 +103,11 @@ template <int ROWS>
 __device__ __forceinline__ void g_fill(unsigned char* hi, unsigned char* lo, const float* __restrict__ src, long long s_row,
                                        long long s_k, int row0, int nrows, int k0, int K, int tid) {
     for (int c = tid; c < ROWS * (GK / 4); c += 128) {
-        const int kc = c & (GK / 4 - 1), r = c / (GK / 4);         // 8 consecutive threads read 8 consecutive K chunks of a row
+        // consecutive threads take consecutive ROWS of one 16-byte K chunk: conflict-free 16-byte shared-memory stores
+        // (the first version had consecutive threads on consecutive chunks of a row: 87 % of its shared-memory wavefronts
+        // were bank conflicts, ncu profiles/r02h); a thread's eight chunks of a row-major operand are one 128-byte line,
+        // and operands addressed with the row index contiguous (the backward GEMMs) load coalesced
+        const int r = c % ROWS, kc = c / ROWS;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         const int row = row0 + r, k = k0 + 4 * kc;
         if (row < nrows) {
@@ -150,14 +155,16 @@ __global__ void __launch_bounds__(128, 1) vr_gemm_tf32x3_kernel(const __grid_con
     // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 [4,6), A = B = TF32 [7,10) [10,13), both K-major,
     // N >> 3 at [17,23), M >> 4 at [24,29)
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(GN >> 3) << 17) | ((uint32_t)(GM >> 4) << 24);
-    const int KB = (p.K + GK - 1) / GK;
+    const int KB_all = (p.K + GK - 1) / GK;
+    const int kb_first = blockIdx.z * p.kb_per_split;
+    const int KB = (KB_all - kb_first < p.kb_per_split) ? (KB_all - kb_first) : p.kb_per_split;     // this slice's K blocks
     for (int kb = 0; kb < KB; ++kb) {
         const int s = kb & 1;
         unsigned char* st = gsm + s * G_STAGE_BYTES;
         unsigned char* a_hi = st, *a_lo = st + GM * GK * 4, *b_hi = st + 2 * GM * GK * 4, *b_lo = b_hi + GN * GK * 4;
         if (kb >= 2) g_mbar_wait(&bar_free[s], (uint32_t)(((kb >> 1) - 1) & 1));    // the MMAs that read this stage have completed
-        g_fill<GM>(a_hi, a_lo, p.A, p.sAm, p.sAk, m0, p.M, kb * GK, p.K, tid);
-        g_fill<GN>(b_hi, b_lo, p.B, p.sBn, p.sBk, n0, p.N, kb * GK, p.K, tid);
+        g_fill<GM>(a_hi, a_lo, p.A, p.sAm, p.sAk, m0, p.M, (kb_first + kb) * GK, p.K, tid);
+        g_fill<GN>(b_hi, b_lo, p.B, p.sBn, p.sBk, n0, p.N, (kb_first + kb) * GK, p.K, tid);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the tensor core's reads
         __syncthreads();
         if (tid == 0) {
@@ -192,7 +199,11 @@ __global__ void __launch_bounds__(128, 1) vr_gemm_tf32x3_kernel(const __grid_con
             if (m < p.M) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
-                    if (n0 + c0 + j < p.N) p.C[(long long)m * p.ldc + n0 + c0 + j] = v[j];
+                    if (n0 + c0 + j < p.N) {
+                        float* dst = p.C + (long long)m * p.ldc + n0 + c0 + j;
+                        if (gridDim.z > 1) atomicAdd(dst, v[j]);        // split K: C was zeroed by the host
+                        else *dst = v[j];
+                    }
             }
         }
     } else {
