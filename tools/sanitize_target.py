@@ -21,5 +21,17 @@ yb = layer(big)
 t = VirtualRadar(wavelength=5e-3, train_wavelength=True, train_radar_location=True, device='cuda:0').to('cuda:0')
 xg = x.clone().requires_grad_(True)
 t(xg).square().mean().backward()                        # adjoint kernels
+# round 2: team-job schedule, notebook up-sampling, tcgen05 STFT (forward + backward)
+from skeleton_action_recognition_b200 import _cabi, pad_frames_notebook
+_cabi.set_schedule(1)
+yt = layer(big)                                         # team-job kernel: 360 jobs on 296 x 2 teams + tickets
+yt2 = layer(x)                                          # fewer jobs than teams
+_cabi.set_schedule(-1)
+assert torch.equal(yt, yb) and torch.equal(yt2, y)
+nb = pad_frames_notebook((torch.randn(50, 17, 3, generator=g, dtype=torch.float64)).cuda(), 6)
+yn = layer17 = None
+k = VirtualRadar(wavelength=5e-3, train_stft_kernel=True, device='cuda:0').to('cuda:0')
+xk = x.clone().requires_grad_(True)
+k(xk).square().mean().backward()                        # tcgen05 GEMM forward + both backward GEMMs + synthesis adjoint
 torch.cuda.synchronize()
 print("ok", float(y.sum()), float(img.sum()), float(yl.sum()), float(il.sum()), float(yu.sum()), float(yo.sum()), float(yb.sum()), float(t.wavelength.grad))
