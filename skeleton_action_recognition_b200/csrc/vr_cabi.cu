@@ -972,7 +972,7 @@ int vr_stft_general_f32(const float* iq_dev, int64_t N, int64_t T, int32_t n_fft
     g.M = (int)M; g.N = K; g.K = K; g.kb_per_split = (K + vr::GK - 1) / vr::GK;
     g.out = out_dev; g.csave = c_save; g.F = F; g.n_fft = n_fft; g.nb = nb;
     dim3 grid((unsigned)((M + vr::GM - 1) / vr::GM), (unsigned)((K + vr::GN - 1) / vr::GN));
-    vr::vr_gemm_tf32x3_kernel<1><<<grid, 128, vr::G_SMEM_BYTES, st>>>(g);
+    vr::vr_gemm_tf32x3_kernel<1><<<grid, vr::G_THREADS, vr::G_SMEM_BYTES, st>>>(g);
     CUDA_TRY(cudaGetLastError());
     return VR_OK;
 }
@@ -1004,7 +1004,7 @@ int vr_stft_general_backward_f32(const float* grad_out_dev, const float* frames_
         g.B = bt_work; g.sBn = 1; g.sBk = K;         // B'(n' = k, k' = n) = Bt[n][k]
         g.M = (int)M; g.N = K; g.K = K; g.C = da_work; g.ldc = K; g.kb_per_split = (K + vr::GK - 1) / vr::GK;
         dim3 grid((unsigned)((M + vr::GM - 1) / vr::GM), (unsigned)((K + vr::GN - 1) / vr::GN));
-        vr::vr_gemm_tf32x3_kernel<0><<<grid, 128, vr::G_SMEM_BYTES, st>>>(g);
+        vr::vr_gemm_tf32x3_kernel<0><<<grid, vr::G_THREADS, vr::G_SMEM_BYTES, st>>>(g);
         CUDA_TRY(cudaMemsetAsync(grad_iq_dev, 0, (size_t)N * T * 2 * sizeof(float), st));
         vr::vr_stft_fold_kernel<<<eb, 256, 0, st>>>(da_work, grad_iq_dev, N, (int)T, F, n_fft, hop);
     }
@@ -1022,7 +1022,7 @@ int vr_stft_general_backward_f32(const float* grad_out_dev, const float* frames_
         splits = (kb_all + g.kb_per_split - 1) / g.kb_per_split;
         if (splits > 1) CUDA_TRY(cudaMemsetAsync(dbt_work, 0, (size_t)K * K * sizeof(float), st));
         dim3 grid((unsigned)((K + vr::GM - 1) / vr::GM), (unsigned)((K + vr::GN - 1) / vr::GN), (unsigned)splits);
-        vr::vr_gemm_tf32x3_kernel<0><<<grid, 128, vr::G_SMEM_BYTES, st>>>(g);
+        vr::vr_gemm_tf32x3_kernel<0><<<grid, vr::G_THREADS, vr::G_SMEM_BYTES, st>>>(g);
         vr::vr_stft_dw_kernel<<<(n_fft * n_fft + 255) / 256, 256, 0, st>>>(dbt_work, grad_wsin_dev, grad_wcos_dev, n_fft, nb);
     }
     CUDA_TRY(cudaGetLastError());

@@ -12,7 +12,7 @@
 // layers/virtual_radar.py:126-129 with nnAudio's imag = -conv(., wsin) -- come out of the same accumulator row.
 //
 // Kernel (`vr_gemm_tf32x3_kernel`): tcgen05.mma kind::tf32, M = 128 x N = 128 x K = 8 per instruction, accumulators in
-// tensor memory, issued by one thread; operands staged in shared memory by the CTA's 128 threads in the canonical
+// tensor memory, issued by one thread; operands staged in shared memory by the CTA's 256 threads in the canonical
 // K-major no-swizzle layout (8 x 16-byte core matrices), two stages, released by tcgen05.commit on mbarriers.
 // float32 accuracy from 10-bit TF32 mantissas by the error-compensated split a = hi + lo (hi = a rounded to TF32 with
 // cvt.rna, lo = a - hi, exact): A.B = Ahi.Bhi + Alo.Bhi + Ahi.Blo -- three MMAs per K step; the dropped lo.lo term is
@@ -32,6 +32,7 @@
 namespace vr {
 
 constexpr int GM = 128, GN = 128, GK = 32;          // CTA tile, K block per stage
+constexpr int G_THREADS = 256;                       // 8 warps stage the operands; warp w reads accumulator lanes 32 (w % 4)
 constexpr int G_ACC = 4;                            // accumulators in tensor memory (G_ACC * GN = 512 columns)
 constexpr int G_STAGE_BYTES = 2 * (GM + GN) * GK * 4;    // hi + lo of the A and B blocks: 64 KB
 constexpr int G_SMEM_BYTES = 2 * G_STAGE_BYTES + 1024;
@@ -102,7 +103,7 @@ __device__ __forceinline__ float tf32_rna(float a) {       // nearest TF32 (ties
 template <int ROWS>
 __device__ __forceinline__ void g_fill(unsigned char* hi, unsigned char* lo, const float* __restrict__ src, long long s_row,
                                        long long s_k, int row0, int nrows, int k0, int K, int tid) {
-    for (int c = tid; c < ROWS * (GK / 4); c += 128) {
+    for (int c = tid; c < ROWS * (GK / 4); c += G_THREADS) {
         // consecutive threads take consecutive ROWS of one 16-byte K chunk: conflict-free 16-byte shared-memory stores
         // (the first version had consecutive threads on consecutive chunks of a row: 87 % of its shared-memory wavefronts
         // were bank conflicts, ncu profiles/r02h); a thread's eight chunks of a row-major operand are one 128-byte line,
@@ -129,7 +130,7 @@ __device__ __forceinline__ void g_fill(unsigned char* hi, unsigned char* lo, con
 }
 
 template <int EPI>
-__global__ void __launch_bounds__(128, 1) vr_gemm_tf32x3_kernel(const __grid_constant__ GemmParams p) {
+__global__ void __launch_bounds__(G_THREADS, 1) vr_gemm_tf32x3_kernel(const __grid_constant__ GemmParams p) {
     extern __shared__ __align__(1024) unsigned char gsm[];
     __shared__ uint64_t bar_free[2], bar_done;
     __shared__ uint32_t tmem_base_s;
@@ -188,12 +189,14 @@ __global__ void __launch_bounds__(128, 1) vr_gemm_tf32x3_kernel(const __grid_con
     g_mbar_wait(&bar_done, 0u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    // ---- epilogue: thread = accumulator row (TMEM lane 32 * warp + lane) ----
-    const int m = m0 + tid;
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    // ---- epilogue: thread = accumulator row (TMEM lane 32 * (warp % 4) + lane); warps 0-3 take the first half of the
+    // columns (bins), warps 4-7 the second half ----
+    const int m = m0 + (tid & 127);
+    const int half = warp >> 2;
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const int steps = KB * (GK / 8), nbig = steps < G_ACC - 1 ? steps : G_ACC - 1;     // big accumulators that hold data
     if (EPI == 0) {
-        for (int c0 = 0; c0 < GN; c0 += 16) {
+        for (int c0 = half * (GN / 2); c0 < (half + 1) * (GN / 2); c0 += 16) {
             float v[16];
             tmem_ld16_sum(trow + c0, nbig, v);
             if (m < p.M) {
@@ -210,7 +213,9 @@ __global__ void __launch_bounds__(128, 1) vr_gemm_tf32x3_kernel(const __grid_con
         // column tile: [re of bins t*nb .. | im of the same bins]; out[(seq * n_fft + ((bin + n_fft/2) % n_fft)) * F + f]
         const int nb = p.nb, tile = blockIdx.y;
         const int seq = m / p.F, f = m - seq * p.F;
-        for (int c0 = 0; c0 < nb; c0 += 16) {
+        const bool split = nb >= 32;                              // 16-column loads: halve the bins only if each half is a multiple
+        const int cb = split ? half * (nb / 2) : 0, ce = split ? cb + nb / 2 : (half == 0 ? nb : 0);
+        for (int c0 = cb; c0 < ce; c0 += 16) {
             float re[16], im[16];
             tmem_ld16_sum(trow + c0, nbig, re);
             tmem_ld16_sum(trow + nb + c0, nbig, im);
