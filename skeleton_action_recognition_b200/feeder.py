@@ -54,17 +54,51 @@ class Dataset(torch.utils.data.Dataset):
         return pad_frames(batch, self.num_pad_frames, self.sigma)
 
 
-def gpu_batches(loader, device, upsample=True, num_pad_frames=None, sigma=None):
+def gpu_batches(loader, device, upsample=True, num_pad_frames=None, sigma=None, prefetch=True):
     """Iterate a DataLoader over `Dataset`: pinned host batch -> asynchronous H2D copy of the RAW samples ->
     up-sampling on the device.  Yields `(x_cuda, labels_cuda)`.  With `upsample=False` the raw batch is
-    yielded (for `Model(num_pad_frames=...)`, which up-samples inside its forward)."""
+    yielded (for `Model(num_pad_frames=...)`, which up-samples inside its forward).
+
+    `prefetch=True` (default): double buffering -- the copy of batch k+1 is issued on a side stream (from a pinned staging
+    copy) while the consumer works on batch k on the current stream; the yielded tensors are made safe to use on the
+    current stream with `wait_stream` / `record_stream`, so the caller needs no extra synchronisation."""
     device = torch.device(device)
     ds = loader.dataset
     k = ds.num_pad_frames if num_pad_frames is None else num_pad_frames
     s = ds.sigma if sigma is None else sigma
-    for x, y in loader:
+
+    def finish(x, y):
+        return (pad_frames(x, k, s) if upsample else x), y
+
+    if not prefetch:
+        for x, y in loader:
+            if not x.is_pinned():
+                x = x.pin_memory()
+            yield finish(x.to(device, non_blocking=True), y.to(device, non_blocking=True))
+        return
+
+    copy_stream = torch.cuda.Stream(device)
+
+    def stage(batch):
+        x, y = batch
         if not x.is_pinned():
             x = x.pin_memory()
-        x = x.to(device, non_blocking=True)
-        y = y.to(device, non_blocking=True)
-        yield (pad_frames(x, k, s) if upsample else x), y
+        with torch.cuda.stream(copy_stream):
+            return x.to(device, non_blocking=True), y.to(device, non_blocking=True), x      # keep the pinned source alive
+
+    it = iter(loader)
+    try:
+        nxt = stage(next(it))
+    except StopIteration:
+        return
+    while nxt is not None:
+        xd, yd, _pinned = nxt
+        try:
+            nxt = stage(next(it))                      # batch k+1 starts copying before batch k is handed out
+        except StopIteration:
+            nxt = None
+        cur = torch.cuda.current_stream(device)
+        cur.wait_stream(copy_stream)                   # batch k's copy is done before anything on the current stream reads it
+        xd.record_stream(cur)
+        yd.record_stream(cur)
+        yield finish(xd, yd)
