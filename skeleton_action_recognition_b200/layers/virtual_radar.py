@@ -229,6 +229,9 @@ class VirtualRadar(torch.nn.Module):
         # before each forward on the same stream neither produces x nor touches the output; consecutive forwards then
         # overlap (a batch starts in the SM slots the previous one has vacated).  Default: plain stream order.
         self.assume_inputs_ready = False
+        # Profiling aid: True wraps every launch of this layer in an NVTX range ("VirtualRadar.<entry>") so that timeline
+        # tools show the fused stage among the model's other kernels (tracing hooks).  Off by default.
+        self.nvtx_ranges = False
 
     # the ctypes arrays are not picklable / deep-copyable (DataParallel.replicate copies __dict__)
     def __getstate__(self):
@@ -313,11 +316,17 @@ class VirtualRadar(torch.nn.Module):
         if N == 0:
             return out, iq
         L = _cabi.lib()
-        with torch.cuda.device(xc.device):
-            stream = ctypes.c_void_p(torch.cuda.current_stream(xc.device).cuda_stream)
-            args = (xc.data_ptr(), N, T, V, M, self._src_c, self._dst_c, len(self.src), self.wavelength.data_ptr(),
-                    self.radar_location.data_ptr(), n_fft, self.hop_length, flags, out.data_ptr())
-            rc = L.vr_forward_debug_f32(*args, iq.data_ptr(), stream) if want_iq else L.vr_forward_f32(*args, stream)
+        if self.nvtx_ranges:
+            torch.cuda.nvtx.range_push("VirtualRadar.forward%s N=%d T=%d" % ("+iq" if want_iq else "", N, T))
+        try:
+            with torch.cuda.device(xc.device):
+                stream = ctypes.c_void_p(torch.cuda.current_stream(xc.device).cuda_stream)
+                args = (xc.data_ptr(), N, T, V, M, self._src_c, self._dst_c, len(self.src), self.wavelength.data_ptr(),
+                        self.radar_location.data_ptr(), n_fft, self.hop_length, flags, out.data_ptr())
+                rc = L.vr_forward_debug_f32(*args, iq.data_ptr(), stream) if want_iq else L.vr_forward_f32(*args, stream)
+        finally:
+            if self.nvtx_ranges:
+                torch.cuda.nvtx.range_pop()
         _cabi.check(rc)
         return out, iq
 
