@@ -483,6 +483,40 @@ def run_ours(args, rank, world, local_rank):
             "fp32_tflops": (55 * T * uk * 24 * M) * un / (ms_f * 1e-3) / 1e12}
         del ux, ubuf
 
+        # ---- BASELINE configs 1 and 3: the notebook's single long sequences (cells 4 / 2 / 3), synthetic data of the same
+        # shape, dtype and bone lists: raw (T, V, 3) array on the device -> utils.pad_frames on the device -> radar ------
+        gait_edges = [(0, 1), (1, 2), (1, 3), (3, 5), (5, 7), (1, 4), (4, 6), (6, 8), (0, 9),
+                      (9, 11), (11, 13), (13, 15), (0, 10), (10, 12), (12, 14), (14, 16)]
+        nb_cases = (("config1_ntu_x550", 300, 25, 550, torch.float32, None, 9e-4),
+                    ("config3_cmu_x20", 2751, 42, 20, torch.float64, [(i, i + 1) for i in range(41)], 5e-3),
+                    ("config3_gait_x10", 8192, 17, 10, torch.float64, gait_edges, 5e-4))
+        notebook = {"op": "virtual_radar_example.ipynb cells 2-4 on the device: pad_frames (utils.py:82-89) + VirtualRadar.forward "
+                          "(VirtualRadar.forward_notebook: two launches), one sequence, synthetic smooth motion of the notebook's shapes"}
+        for name, t_raw, v_n, kpad, dt, eds, lam in nb_cases:
+            gq = torch.Generator().manual_seed(t_raw)
+            tt = torch.linspace(0, 6.28, t_raw, dtype=torch.float64)[:, None, None]
+            raw = (torch.randn(1, v_n, 3, generator=gq, dtype=torch.float64) * 0.3
+                   + 0.1 * torch.sin(tt * (1 + torch.arange(v_n, dtype=torch.float64)[None, :, None] / v_n))).to(dt)
+            kw = dict(wavelength=lam, device=dev)
+            if eds is not None:
+                kw["edges"] = eds
+            lay = VirtualRadar(**kw).to(dev)
+            rd = raw.to(dev)
+            ms_nb = timed(lambda: lay.forward_notebook(rd, kpad), 10)
+            entry = {"raw_frames": t_raw, "joints": v_n, "frames_at_radar_rate": t_raw * kpad, "ms": ms_nb,
+                     "out_shape": [1, N_FFT, t_raw * kpad // HOP + 1]}
+            if name == "config1_ntu_x550" and not args.no_cpu_baseline:
+                from oracle import pad_frames as opf2, virtual_radar_oracle as vro2
+                t0 = time.perf_counter()
+                xo = opf2.notebook_tensor(opf2.pad_frames(raw.numpy(), num_pad_frames=kpad))
+                vro2.forward(xo, wavelength=lam)
+                dtc = time.perf_counter() - t0
+                entry["cpu_baseline"] = {"value": dtc * 1e3, "unit": "ms", "cores": torch.get_num_threads(), "kind": "port",
+                                         "sample": "scipy pad_frames + the reference's forward (oracle port), once"}
+            notebook[name] = entry
+            del lay, rd
+        next_rows["notebook_configs"] = notebook
+
         # ---- BASELINE config 5: the consumer's training step with the fused input stage ----------
         from skeleton_action_recognition_b200.models.resnet import Model
         tb = 64

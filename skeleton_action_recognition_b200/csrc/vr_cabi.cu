@@ -706,7 +706,19 @@ int vr_pad_frames_joints(const void* x_dev, int32_t x_is_f64, int64_t N, int64_t
             attr_done[dev] = true;
         }
     }
-    const int grid = (int)std::min<long long>(N * p.ncb, (long long)sm_count * 4);
+    // row slices: only when the per-unit preamble (Gaussian + sequential spline solve, ~50 cycles per frame) is cheap next to
+    // the evaluation (a latency-bound chain of conversions and FP64 operations: ~500 cycles per value and thread were
+    // measured with one CTA per SM), and only up to one wave of CTAs
+    {
+        const long long KT = (long long)num_pad_frames * T;
+        const double solve_cost = 50.0 * (double)T, eval_cost = 500.0 * (double)KT * p.nc / 1024.0;
+        long long nrs = std::min<long long>(std::max<long long>(1, sm_count / std::max<long long>(1, N * p.ncb)),
+                                            std::max<long long>(1, (long long)(eval_cost / (2.0 * solve_cost))));
+        nrs = std::min<long long>(nrs, std::max<long long>(1, KT / 1024));
+        p.nrs = (int)nrs;
+        p.rows_per_slice = (KT + nrs - 1) / nrs;
+    }
+    const int grid = (int)std::min<long long>(N * p.ncb * p.nrs, (long long)sm_count * 4);
     if (x_is_f64) vr::vr_pad_frames_nb_kernel<double><<<grid, 1024, smem, (cudaStream_t)stream>>>(p);
     else vr::vr_pad_frames_nb_kernel<float><<<grid, 1024, smem, (cudaStream_t)stream>>>(p);
     CUDA_TRY(cudaGetLastError());

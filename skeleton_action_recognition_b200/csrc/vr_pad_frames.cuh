@@ -182,6 +182,8 @@ struct PadNbParams {
     float* out;
     long long N;
     int T, V, C, K, nc, ncb, planar;
+    int nrs;                     // row slices per (sequence, column block): a single long sequence still fills the machine
+    long long rows_per_slice;
     int radius;
     double ratio;
     double w[PF_MAX_RADIUS + 1];
@@ -198,11 +200,17 @@ __global__ void __launch_bounds__(1024, 1) vr_pad_frames_nb_kernel(const __grid_
     const int tid = threadIdx.x;
     const long long KT = (long long)p.K * T;
 
-    for (long long unit = blockIdx.x; unit < p.N * p.ncb; unit += gridDim.x) {
-        const long long n = unit / p.ncb;
-        const int col0 = (int)(unit - n * p.ncb) * nc;
+    for (long long unit = blockIdx.x; unit < p.N * p.ncb * p.nrs; unit += gridDim.x) {
+        // unit = (sequence, column block, row slice); the Gaussian and the spline solve are repeated per row slice (the host
+        // only slices when they are cheap next to the evaluation: one NTU sequence x550 is 2 column blocks x 165 000 rows)
+        const long long nb_unit = unit / p.nrs;
+        const int rs = (int)(unit - nb_unit * p.nrs);
+        const long long n = nb_unit / p.ncb;
+        const int col0 = (int)(nb_unit - n * p.ncb) * nc;
         const int ncl = (VC - col0 < nc) ? (VC - col0) : nc;
         const TIN* xp = static_cast<const TIN*>(p.x) + n * (long long)T * VC;
+        const long long row_lo = rs * p.rows_per_slice;
+        const long long row_hi = (row_lo + p.rows_per_slice < KT) ? row_lo + p.rows_per_slice : KT;
         __syncthreads();
 
         // (1) Gaussian along the joints of every frame: scipy's correlate1d order (centre tap, then symmetric pairs
@@ -225,26 +233,53 @@ __global__ void __launch_bounds__(1024, 1) vr_pad_frames_nb_kernel(const __grid_
         }
         __syncthreads();
 
-        // (2) not-a-knot cubic spline in time, one thread per column (same elimination as vr_pad_frames_kernel)
+        // (2) not-a-knot cubic spline in time (same elimination, same order of operations as vr_pad_frames_kernel).  The
+        // right-hand sides do not depend on the recurrence: all threads compute them first (into Msh), so that the one thread
+        // per column that runs the two sequential sweeps has a single load per step in front of its DADD -> DMUL chain
+        // and the loads of the next steps are already in flight (the mocap files have 2751 / 8192 frames per column).
+        for (int idx = tid; idx < (T - 2) * ncl; idx += blockDim.x) {
+            const int i = 1 + idx / ncl, c = idx - (i - 1) * ncl;
+            Msh[i * nc + c] = 6.0 * ((ys[(i - 1) * nc + c] - 2.0 * ys[i * nc + c]) + ys[(i + 1) * nc + c]);
+        }
+        __syncthreads();
         if (tid < ncl) {
             const int c = tid;
-            auto rhs = [&](int i) { return 6.0 * ((ys[(i - 1) * nc + c] - 2.0 * ys[i * nc + c]) + ys[(i + 1) * nc + c]); };
-            const double M1 = rhs(1) / 6.0, Mn = rhs(T - 2) / 6.0;
+            const double M1 = Msh[1 * nc + c] / 6.0, Mn = Msh[(T - 2) * nc + c] / 6.0;
+            __syncwarp(__activemask());
             Msh[1 * nc + c] = M1;
             Msh[(T - 2) * nc + c] = Mn;
             double d = 0.0;
-            for (int i = 2; i <= T - 3; ++i) {
-                double r = rhs(i);
+            int i = 2;
+            for (; i + 3 <= T - 4; i += 4) {                      // interior steps, four loads ahead of the chain
+                double r0 = Msh[i * nc + c], r1 = Msh[(i + 1) * nc + c], r2 = Msh[(i + 2) * nc + c], r3 = Msh[(i + 3) * nc + c];
+                const double c0 = cp[i], c1 = cp[i + 1], c2 = cp[i + 2], c3 = cp[i + 3];
+                if (i == 2) r0 -= M1;
+                d = (r0 - d) * c0; Msh[i * nc + c] = d;
+                d = (r1 - d) * c1; Msh[(i + 1) * nc + c] = d;
+                d = (r2 - d) * c2; Msh[(i + 2) * nc + c] = d;
+                d = (r3 - d) * c3; Msh[(i + 3) * nc + c] = d;
+            }
+            for (; i <= T - 3; ++i) {
+                double r = Msh[i * nc + c];
                 if (i == 2) r -= M1;
                 if (i == T - 3) r -= Mn;
                 d = (r - d) * cp[i];
                 Msh[i * nc + c] = d;
             }
             double next = 0.0;
-            for (int i = T - 3; i >= 2; --i) {
-                const double m = Msh[i * nc + c] - (i == T - 3 ? 0.0 : cp[i] * next);
-                Msh[i * nc + c] = m;
-                next = m;
+            i = T - 3;
+            if (i >= 2) { next = Msh[i * nc + c]; --i; }           // M_{T-3} = d'_{T-3}
+            for (; i - 3 >= 2; i -= 4) {
+                const double d0 = Msh[i * nc + c], d1 = Msh[(i - 1) * nc + c], d2 = Msh[(i - 2) * nc + c], d3 = Msh[(i - 3) * nc + c];
+                const double c0 = cp[i], c1 = cp[i - 1], c2 = cp[i - 2], c3 = cp[i - 3];
+                next = d0 - c0 * next; Msh[i * nc + c] = next;
+                next = d1 - c1 * next; Msh[(i - 1) * nc + c] = next;
+                next = d2 - c2 * next; Msh[(i - 2) * nc + c] = next;
+                next = d3 - c3 * next; Msh[(i - 3) * nc + c] = next;
+            }
+            for (; i >= 2; --i) {
+                next = Msh[i * nc + c] - cp[i] * next;
+                Msh[i * nc + c] = next;
             }
             Msh[0 * nc + c] = 2.0 * Msh[1 * nc + c] - Msh[2 * nc + c];
             Msh[(T - 1) * nc + c] = 2.0 * Msh[(T - 2) * nc + c] - Msh[(T - 3) * nc + c];
@@ -260,7 +295,7 @@ __global__ void __launch_bounds__(1024, 1) vr_pad_frames_nb_kernel(const __grid_
         const long long ostride = p.planar ? p.V : VC;
         int jc = -1;
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        for (long long i = tid / ncl; i < KT && tid < rows_per_step * ncl; i += rows_per_step) {
+        for (long long i = row_lo + tid / ncl; i < row_hi && tid < rows_per_step * ncl; i += rows_per_step) {
             int j;
             double tt;
             pf_locate(i, p.ratio, T, j, tt);
