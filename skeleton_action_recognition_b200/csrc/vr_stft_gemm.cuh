@@ -32,7 +32,11 @@
 namespace vr {
 
 constexpr int GM = 128, GN = 128, GK = 32;          // CTA tile, K block per stage
-constexpr int G_THREADS = 256;                       // 8 warps stage the operands; warp w reads accumulator lanes 32 (w % 4)
+#ifndef VR_GEMM_THREADS
+#define VR_GEMM_THREADS 1024
+#endif
+constexpr int G_THREADS = VR_GEMM_THREADS;           // all warps stage the operands; warp w reads accumulator lanes 32 (w % 4)
+constexpr int G_PARTS = G_THREADS / 128;             // ... and the (w / 4)-th part of the columns in the epilogue
 constexpr int G_ACC = 4;                            // accumulators in tensor memory (G_ACC * GN = 512 columns)
 constexpr int G_STAGE_BYTES = 2 * (GM + GN) * GK * 4;    // hi + lo of the A and B blocks: 64 KB
 constexpr int G_SMEM_BYTES = 2 * G_STAGE_BYTES + 1024;
@@ -43,7 +47,7 @@ struct GemmParams {
     int M, N, K;
     int kb_per_split;                               // K blocks per gridDim.z slice (EPI 0 accumulates with atomics when gridDim.z > 1)
     float* C; long long ldc;                        // EPI 0: C[m * ldc + n]
-    float* out; float* csave;                       // EPI 1: (sequences, n_fft, F) log-magnitude; optional raw C (M x N)
+    float* out; float* csave;                       // EPI 1: (sequences, n_fft, F) log-magnitude; optional raw C, column-major (N x ldc)
     int F, n_fft, nb;                               // frames per sequence; bins per column tile (re block | im block)
 };
 
@@ -99,16 +103,41 @@ __device__ __forceinline__ float tf32_rna(float a) {       // nearest TF32 (ties
     return __uint_as_float(r);
 }
 // one operand block (ROWS x GK) from global memory into the canonical layout, split into hi / lo:
-// element (r, k) at (k / 4) * (ROWS * 16) + r * 16 + (k % 4) * 4
+// element (r, k) at (k / 4) * (ROWS * 16) + r * 16 + (k % 4) * 4.  Two halves, so that the loads of the block after next
+// are in flight while this one is split and multiplied (the loop was bound by the latency of these loads: ncu
+// profiles/r02s, long-scoreboard 18 of 30 stall cycles per issue): g_load into registers, g_split from them.
+// consecutive threads take consecutive ROWS of one 16-byte K chunk: conflict-free 16-byte shared-memory stores
+// (the first version had consecutive threads on consecutive chunks of a row: 87 % of its shared-memory wavefronts
+// were bank conflicts, ncu profiles/r02h); a thread's eight chunks of a row-major operand are one 128-byte line,
+// and operands addressed with the row index contiguous (the backward GEMMs) load coalesced
+// which 16-byte chunk (row r, K chunk kc) of the block a thread moves.  The shared-memory store is conflict-free when the
+// eight lanes of a quarter warp hold eight consecutive rows of one chunk (row r sits at byte 16 r of its chunk plane).
+//  - K contiguous in memory (row-major operand): a warp = 8 rows x 4 adjacent chunks, i.e. 8 lines with two whole
+//    sectors each.  (32 rows x 1 chunk, the first mapping, made every load instruction touch 32 lines: the L1 tag stage
+//    ran at 84 % of its peak and bounded the loop, ncu profiles/r02t.)
+//  - rows contiguous in memory (the transposed operands of the backward GEMMs): a warp = 32 rows x 1 chunk, whose four
+//    scalar loads are one line each.
 template <int ROWS>
-__device__ __forceinline__ void g_fill(unsigned char* hi, unsigned char* lo, const float* __restrict__ src, long long s_row,
-                                       long long s_k, int row0, int nrows, int k0, int K, int tid) {
-    for (int c = tid; c < ROWS * (GK / 4); c += G_THREADS) {
-        // consecutive threads take consecutive ROWS of one 16-byte K chunk: conflict-free 16-byte shared-memory stores
-        // (the first version had consecutive threads on consecutive chunks of a row: 87 % of its shared-memory wavefronts
-        // were bank conflicts, ncu profiles/r02h); a thread's eight chunks of a row-major operand are one 128-byte line,
-        // and operands addressed with the row index contiguous (the backward GEMMs) load coalesced
-        const int r = c % ROWS, kc = c / ROWS;
+__device__ __forceinline__ void g_chunk(int c, bool k_contig, int& r, int& kc) {
+    if (k_contig) {
+        const int lane = c & 31, w = c >> 5;                  // warp-sized group w: rows 8 (w % (ROWS/8)) .., chunks 4 (w / (ROWS/8)) ..
+        r = 8 * (w % (ROWS / 8)) + (lane & 7);
+        kc = 4 * (w / (ROWS / 8)) + (lane >> 3);
+    } else {
+        r = c % ROWS;
+        kc = c / ROWS;
+    }
+}
+template <int ROWS>
+struct GFrag { float4 v[ROWS * (GK / 4) / G_THREADS]; };
+template <int ROWS>
+__device__ __forceinline__ void g_load(GFrag<ROWS>& f, const float* __restrict__ src, long long s_row, long long s_k, int row0,
+                                       int nrows, int k0, int K, int tid) {
+    static_assert(ROWS * (GK / 4) % G_THREADS == 0, "whole chunks per thread");
+#pragma unroll
+    for (int i = 0; i < ROWS * (GK / 4) / G_THREADS; ++i) {
+        int r, kc;
+        g_chunk<ROWS>(tid + i * G_THREADS, s_k == 1, r, kc);
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         const int row = row0 + r, k = k0 + 4 * kc;
         if (row < nrows) {
@@ -121,6 +150,16 @@ __device__ __forceinline__ void g_fill(unsigned char* hi, unsigned char* lo, con
                 if (k + 3 < K) v.w = __ldg(p + 3 * s_k);
             }
         }
+        f.v[i] = v;
+    }
+}
+template <int ROWS>
+__device__ __forceinline__ void g_split(unsigned char* hi, unsigned char* lo, const GFrag<ROWS>& f, bool k_contig, int tid) {
+#pragma unroll
+    for (int i = 0; i < ROWS * (GK / 4) / G_THREADS; ++i) {
+        int r, kc;
+        g_chunk<ROWS>(tid + i * G_THREADS, k_contig, r, kc);
+        const float4 v = f.v[i];
         const float4 h = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
         const float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);       // exact
         const int off = kc * (ROWS * 16) + r * 16;
@@ -135,7 +174,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) vr_gemm_tf32x3_kernel(const __gr
     __shared__ uint64_t bar_free[2], bar_done;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int m0 = blockIdx.x * GM, n0 = blockIdx.y * GN;
+    const int ntn = (p.N + GN - 1) / GN;                         // column tiles fastest: the CTAs that share an A tile run together
+    const int tile_n = blockIdx.x % ntn, tile_m = blockIdx.x / ntn;    // (A once from HBM; it was read once per column tile, ncu r02s)
+    const int m0 = tile_m * GM, n0 = tile_n * GN;
 
     if (tid == 0) {
         for (int i = 0; i < 2; ++i)
@@ -159,13 +200,26 @@ __global__ void __launch_bounds__(G_THREADS, 1) vr_gemm_tf32x3_kernel(const __gr
     const int KB_all = (p.K + GK - 1) / GK;
     const int kb_first = blockIdx.z * p.kb_per_split;
     const int KB = (KB_all - kb_first < p.kb_per_split) ? (KB_all - kb_first) : p.kb_per_split;     // this slice's K blocks
-    for (int kb = 0; kb < KB; ++kb) {
+    GFrag<GM> fa[2];
+    GFrag<GN> fb[2];
+    const int k_first = kb_first * GK;
+    g_load<GM>(fa[0], p.A, p.sAm, p.sAk, m0, p.M, k_first, p.K, tid);
+    g_load<GN>(fb[0], p.B, p.sBn, p.sBk, n0, p.N, k_first, p.K, tid);
+    if (KB > 1) {
+        g_load<GM>(fa[1], p.A, p.sAm, p.sAk, m0, p.M, k_first + GK, p.K, tid);
+        g_load<GN>(fb[1], p.B, p.sBn, p.sBk, n0, p.N, k_first + GK, p.K, tid);
+    }
+    auto k_block = [&](const int kb, GFrag<GM>& ra, GFrag<GN>& rb) {
         const int s = kb & 1;
         unsigned char* st = gsm + s * G_STAGE_BYTES;
         unsigned char* a_hi = st, *a_lo = st + GM * GK * 4, *b_hi = st + 2 * GM * GK * 4, *b_lo = b_hi + GN * GK * 4;
         if (kb >= 2) g_mbar_wait(&bar_free[s], (uint32_t)(((kb >> 1) - 1) & 1));    // the MMAs that read this stage have completed
-        g_fill<GM>(a_hi, a_lo, p.A, p.sAm, p.sAk, m0, p.M, (kb_first + kb) * GK, p.K, tid);
-        g_fill<GN>(b_hi, b_lo, p.B, p.sBn, p.sBk, n0, p.N, (kb_first + kb) * GK, p.K, tid);
+        g_split<GM>(a_hi, a_lo, ra, p.sAk == 1, tid);
+        g_split<GN>(b_hi, b_lo, rb, p.sBk == 1, tid);
+        if (kb + 2 < KB) {                                        // the block after next: in flight over two barriers
+            g_load<GM>(ra, p.A, p.sAm, p.sAk, m0, p.M, k_first + (kb + 2) * GK, p.K, tid);
+            g_load<GN>(rb, p.B, p.sBn, p.sBk, n0, p.N, k_first + (kb + 2) * GK, p.K, tid);
+        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the tensor core's reads
         __syncthreads();
         if (tid == 0) {
@@ -185,18 +239,22 @@ __global__ void __launch_bounds__(G_THREADS, 1) vr_gemm_tf32x3_kernel(const __gr
             umma_commit(&bar_free[s]);                            // arrives when the MMAs issued so far have read shared memory
             if (kb == KB - 1) umma_commit(&bar_done);
         }
+    };
+    for (int kb = 0; kb < KB; kb += 2) {
+        k_block(kb, fa[0], fb[0]);
+        if (kb + 1 < KB) k_block(kb + 1, fa[1], fb[1]);
     }
     g_mbar_wait(&bar_done, 0u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    // ---- epilogue: thread = accumulator row (TMEM lane 32 * (warp % 4) + lane); warps 0-3 take the first half of the
-    // columns (bins), warps 4-7 the second half ----
+    // ---- epilogue: thread = accumulator row (TMEM lane 32 * (warp % 4) + lane); the warps of each group of four take one
+    // part of the columns (bins) ----
     const int m = m0 + (tid & 127);
-    const int half = warp >> 2;
+    const int part = warp >> 2;
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const int steps = KB * (GK / 8), nbig = steps < G_ACC - 1 ? steps : G_ACC - 1;     // big accumulators that hold data
     if (EPI == 0) {
-        for (int c0 = half * (GN / 2); c0 < (half + 1) * (GN / 2); c0 += 16) {
+        for (int c0 = part * (GN / G_PARTS); c0 < (part + 1) * (GN / G_PARTS); c0 += 16) {
             float v[16];
             tmem_ld16_sum(trow + c0, nbig, v);
             if (m < p.M) {
@@ -211,10 +269,11 @@ __global__ void __launch_bounds__(G_THREADS, 1) vr_gemm_tf32x3_kernel(const __gr
         }
     } else {
         // column tile: [re of bins t*nb .. | im of the same bins]; out[(seq * n_fft + ((bin + n_fft/2) % n_fft)) * F + f]
-        const int nb = p.nb, tile = blockIdx.y;
+        const int nb = p.nb, tile = tile_n;
         const int seq = m / p.F, f = m - seq * p.F;
-        const bool split = nb >= 32;                              // 16-column loads: halve the bins only if each half is a multiple
-        const int cb = split ? half * (nb / 2) : 0, ce = split ? cb + nb / 2 : (half == 0 ? nb : 0);
+        const int parts = (nb / 16 < G_PARTS) ? (nb / 16 > 0 ? nb / 16 : 1) : G_PARTS;      // 16-column loads: every part a multiple of 16 bins
+        const int per = (nb / parts + 15) / 16 * 16;
+        const int cb = part < parts ? part * per : 0, ce = part < parts ? (cb + per < nb ? cb + per : nb) : 0;
         for (int c0 = cb; c0 < ce; c0 += 16) {
             float re[16], im[16];
             tmem_ld16_sum(trow + c0, nbig, re);
@@ -228,8 +287,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) vr_gemm_tf32x3_kernel(const __gr
                         const int row = (bin + p.n_fft / 2) % p.n_fft;
                         p.out[((long long)seq * p.n_fft + row) * p.F + f] = logf(mag + 1e-6f);
                         if (p.csave) {
-                            p.csave[(long long)m * p.N + n0 + c0 + j] = re[j];
-                            p.csave[(long long)m * p.N + n0 + nb + c0 + j] = im[j];
+                            p.csave[(long long)(n0 + c0 + j) * p.ldc + m] = re[j];          // column-major: lanes = rows, coalesced
+                            p.csave[(long long)(n0 + nb + c0 + j) * p.ldc + m] = im[j];
                         }
                     }
                 }
@@ -275,21 +334,21 @@ __global__ void vr_stft_bt_kernel(const float* __restrict__ wsin, const float* _
 }
 // backward of ln(|X| + 1e-6) and the roll: dC from grad_out and the saved Re / Im
 __global__ void vr_stft_dc_kernel(const float* __restrict__ gout, const float* __restrict__ csave, float* __restrict__ dC,
-                                  long long M, int F, int n_fft, int nb) {
+                                  long long M, long long ldm, int F, int n_fft, int nb) {
+    // C and dC are column-major (2 n_fft columns of ldm floats): threads run along the rows, every access coalesced
     const long long total = M * n_fft;
-    const int N = 2 * n_fft;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int bin = (int)(i % n_fft);
-        const long long m = i / n_fft;
+        const long long m = i % M;
+        const int bin = (int)(i / M);
         const long long seq = m / F;
         const int f = (int)(m - seq * F);
         const int cr = stft_row_re(bin, nb), ci = stft_row_im(bin, nb);
-        const float re = csave[m * N + cr], im = csave[m * N + ci];
+        const float re = csave[cr * ldm + m], im = csave[ci * ldm + m];
         const float g = __ldg(gout + (seq * n_fft + (bin + n_fft / 2) % n_fft) * F + f);
         const float mag = sqrtf(fmaf(re, re, im * im));
         const float w = mag > 0.f ? g / ((mag + 1e-6f) * mag) : 0.f;
-        dC[m * N + cr] = w * re;
-        dC[m * N + ci] = w * im;
+        dC[cr * ldm + m] = w * re;
+        dC[ci * ldm + m] = w * im;
     }
 }
 // overlap-add of the frame gradients through the reflect padding: dA (S*F, 2 n_fft) -> grad_iq (S, T, 2), zeroed by the caller

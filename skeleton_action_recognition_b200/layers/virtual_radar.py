@@ -71,7 +71,7 @@ class _STFTKernels(torch.nn.Module):
         (vr_stft_general_backward_f32).  iq (N,T,2) CUDA float32 -> (N, n_fft, T//hop+1)."""
         if not iq.is_cuda:
             raise RuntimeError("the general-kernel STFT (B200) has no CPU path")
-        return _GeneralSTFTFunction.apply(iq, self.wsin, self.wcos, self.n_fft, self.stride)
+        return _GeneralSTFTFunction.apply(iq, self.wsin, self.wcos, self.n_fft, self.stride, torch.is_grad_enabled())
 
     def _logmag_torch(self, iq):
         """TEST CROSS-CHECK ONLY (never called by forward): the same computation with torch ops (cuBLAS GEMM + autograd)."""
@@ -92,7 +92,7 @@ class _GeneralSTFTFunction(torch.autograd.Function):
     csrc/vr_stft_gemm.cuh behind vr_stft_general_f32 / vr_stft_general_backward_f32 (no library GEMM, no autograd graph)."""
 
     @staticmethod
-    def forward(ctx, iq, wsin, wcos, n_fft, hop):
+    def forward(ctx, iq, wsin, wcos, n_fft, hop, grad_mode):
         iq = iq.contiguous()
         if iq.dtype != torch.float32 or wsin.dtype != torch.float32:
             raise ValueError("the general-kernel STFT computes in float32")
@@ -103,7 +103,8 @@ class _GeneralSTFTFunction(torch.autograd.Function):
         dev = iq.device
         frames = torch.empty(max(int(parts[0]), 1), dtype=torch.float32, device=dev)
         bt = torch.empty(max(int(parts[1]), 1), dtype=torch.float32, device=dev)
-        need = any(ctx.needs_input_grad[:3])
+        # needs_input_grad ignores torch.no_grad(): the caller passes the grad mode, so that inference does not write Re / Im
+        need = bool(grad_mode) and any(ctx.needs_input_grad[:3])
         csave = torch.empty(max(int(parts[2]), 1), dtype=torch.float32, device=dev) if need else None
         out = torch.empty((N, n_fft, T // hop + 1), dtype=torch.float32, device=dev)
         if N > 0:
@@ -139,7 +140,7 @@ class _GeneralSTFTFunction(torch.autograd.Function):
                                                               N, T, n_fft, hop, dc.data_ptr(), ptr(da), ptr(dbt),
                                                               ptr(giq), ptr(gsin), ptr(gcos), stream)
             _cabi.check(rc)
-        return (giq, gsin if ctx.needs_input_grad[1] else None, gcos if ctx.needs_input_grad[2] else None, None, None)
+        return (giq, gsin if ctx.needs_input_grad[1] else None, gcos if ctx.needs_input_grad[2] else None, None, None, None)
 
 
 class _RadarFunction(torch.autograd.Function):
