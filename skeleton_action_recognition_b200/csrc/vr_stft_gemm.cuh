@@ -12,10 +12,11 @@
 // layers/virtual_radar.py:126-129 with nnAudio's imag = -conv(., wsin) -- come out of the same accumulator row.
 //
 // Kernel (`vr_gemm_tf32x3_kernel`): tcgen05.mma kind::tf32, M = 128 x N = 128 x K = 8 per instruction, accumulators in
-// tensor memory, issued by one thread; operands staged in shared memory by the CTA's 256 threads in the canonical
-// K-major no-swizzle layout (8 x 16-byte core matrices), two stages, released by tcgen05.commit on mbarriers.
-// float32 accuracy from 10-bit TF32 mantissas by the error-compensated split a = hi + lo (hi = a rounded to TF32 with
-// cvt.rna, lo = a - hi, exact): A.B = Ahi.Bhi + Alo.Bhi + Ahi.Blo -- three MMAs per K step; the dropped lo.lo term is
+// tensor memory, issued by one thread; operands staged in shared memory by the CTA's 1024 threads in the canonical
+// K-major 128-byte-swizzled layout, three stages, handed over on mbarriers (full: the warps'
+// arrivals; free: tcgen05.commit).
+// float32 accuracy from 10-bit TF32 mantissas by the error-compensated split a = hi + lo (hi = a rounded to TF32,
+// nearest / ties away, lo = a - hi, exact): A.B = Ahi.Bhi + Alo.Bhi + Ahi.Blo -- three MMAs per K step; the dropped lo.lo term is
 // 2^-22 relative.  The tensor core ACCUMULATES with truncation, one truncation per instruction: with all 3 x K/8 = 192
 // instructions adding into one accumulator the first version was biased by ~4e-6 relative (measured, profiles/r02h).
 // Hence FOUR accumulators in the 512 tensor-memory columns: the hi.hi products rotate over three of them (21
@@ -32,14 +33,16 @@
 namespace vr {
 
 constexpr int GM = 128, GN = 128, GK = 32;          // CTA tile, K block per stage
-#ifndef VR_GEMM_THREADS
-#define VR_GEMM_THREADS 1024
-#endif
-constexpr int G_THREADS = VR_GEMM_THREADS;           // all warps stage the operands; warp w reads accumulator lanes 32 (w % 4)
-constexpr int G_PARTS = G_THREADS / 128;             // ... and the (w / 4)-th part of the columns in the epilogue
+constexpr int G_THREADS = 1024;                     // every thread stages one 16-byte chunk of A and one of B per K block;
+constexpr int G_WARPS = G_THREADS / 32;             // warp w reads accumulator lanes 32 (w % 4) and the (w / 4)-th part of
+constexpr int G_PARTS = G_THREADS / 128;            // the columns in the epilogue
 constexpr int G_ACC = 4;                            // accumulators in tensor memory (G_ACC * GN = 512 columns)
+constexpr int G_STAGES = 3;
 constexpr int G_STAGE_BYTES = 2 * (GM + GN) * GK * 4;    // hi + lo of the A and B blocks: 64 KB
-constexpr int G_SMEM_BYTES = 2 * G_STAGE_BYTES + 1024;
+constexpr int G_SMEM_BYTES = G_STAGES * G_STAGE_BYTES + 1024;
+static_assert(GM * (GK / 4) == G_THREADS && GN * (GK / 4) == G_THREADS, "one chunk of each operand per thread");
+static_assert(GK * 4 == 128, "a K block is one 128-byte swizzle line per row");
+static_assert(GK / 8 >= G_ACC - 1, "every K block touches all accumulators");
 
 struct GemmParams {
     const float* A; long long sAm, sAk;             // A(m, k) = A[m * sAm + k * sAk]
@@ -52,12 +55,13 @@ struct GemmParams {
 };
 
 #ifdef __CUDACC__
-__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t saddr) {
     // cute::UMMA::SmemDescriptor: start address [0,14), leading byte offset [16,30), stride byte offset [32,46) (all >> 4),
-    // version [46,48) = 1 on Blackwell, layout type [61,64) = 0 (no swizzle).  K-major, no swizzle: LBO = distance
-    // between the two 16-byte K chunks of an instruction, SBO = distance between 8-row groups.
-    return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
+    // version [46,48) = 1 on Blackwell, layout type [61,64) = 2 (SWIZZLE_128B).  K-major, 128-byte swizzle: a row is one
+    // 128-byte line whose 16-byte chunks are XOR-ed with (row % 8) -- the hardware applies it to address bits [4,7) ^
+    // [7,10), so the block must be 1024-byte aligned; SBO = 1024 = distance between 8-row groups; LBO is not used (the
+    // K = 8 of one instruction lies inside the line); a K step advances the start address by 32 bytes.
+    return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
@@ -66,28 +70,40 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
+// tensor memory -> registers, 32 lanes x W columns (W = 8 or 16); the caller waits once for all its loads
+template <int W>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[W]);
+template <>
+__device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, float (&v)[16]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]),
+                   "=f"(v[8]), "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
                  : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
-// one row's 16 columns summed over the accumulators that were used (the first `nacc` big ones and the small one)
-__device__ __forceinline__ void tmem_ld16_sum(uint32_t taddr, int nbig, float (&v)[16]) {
-    tmem_ld16(taddr, v);
-    float w[16];
-    for (int a = 1; a < nbig; ++a) {
-        tmem_ld16(taddr + a * GN, w);
+template <>
+__device__ __forceinline__ void tmem_ld<8>(uint32_t taddr, float (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// one row's W columns summed over the four accumulators: the four loads are in flight together
+template <int W>
+__device__ __forceinline__ void tmem_ld_sum(uint32_t taddr, float (&v)[W]) {
+    float a1[W], a2[W], a3[W];
+    tmem_ld<W>(taddr, v);
+    tmem_ld<W>(taddr + GN, a1);
+    tmem_ld<W>(taddr + 2 * GN, a2);
+    tmem_ld<W>(taddr + 3 * GN, a3);
+    tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] += w[i];
-    }
-    tmem_ld16(taddr + (G_ACC - 1) * GN, w);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] += w[i];
+    for (int i = 0; i < W; ++i) v[i] = ((v[i] + a1[i]) + a2[i]) + a3[i];
+}
+__device__ __forceinline__ void g_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void g_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
 }
 __device__ __forceinline__ void g_mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
@@ -97,52 +113,59 @@ __device__ __forceinline__ void g_mbar_wait(uint64_t* bar, uint32_t parity) {
     } while (!ok);
 }
 
-__device__ __forceinline__ float tf32_rna(float a) {       // nearest TF32 (ties away): the split's lo part is then sign-symmetric
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(a));
-    return __uint_as_float(r);
+// a = hi + lo with hi = a rounded to TF32 (10-bit mantissa), nearest with ties away from zero -- what cvt.rna.tf32.f32
+// gives for every finite a that does not round up to infinity -- and lo = a - hi, exact.  Two integer instructions (the
+// cvt is emulated with four on this target).  Ties away keeps the lo parts sign-symmetric.
+__device__ __forceinline__ void tf32_split(float a, float& hi, float& lo) {
+    hi = __uint_as_float((__float_as_uint(a) + 0x1000u) & 0xffffe000u);
+    lo = a - hi;
 }
-// one operand block (ROWS x GK) from global memory into the canonical layout, split into hi / lo:
-// element (r, k) at (k / 4) * (ROWS * 16) + r * 16 + (k % 4) * 4.  Two halves, so that the loads of the block after next
-// are in flight while this one is split and multiplied (the loop was bound by the latency of these loads: ncu
-// profiles/r02s, long-scoreboard 18 of 30 stall cycles per issue): g_load into registers, g_split from them.
-// consecutive threads take consecutive ROWS of one 16-byte K chunk: conflict-free 16-byte shared-memory stores
-// (the first version had consecutive threads on consecutive chunks of a row: 87 % of its shared-memory wavefronts
-// were bank conflicts, ncu profiles/r02h); a thread's eight chunks of a row-major operand are one 128-byte line,
-// and operands addressed with the row index contiguous (the backward GEMMs) load coalesced
-// which 16-byte chunk (row r, K chunk kc) of the block a thread moves.  The shared-memory store is conflict-free when the
-// eight lanes of a quarter warp hold eight consecutive rows of one chunk (row r sits at byte 16 r of its chunk plane).
-//  - K contiguous in memory (row-major operand): a warp = 8 rows x 4 adjacent chunks, i.e. 8 lines with two whole
-//    sectors each.  (32 rows x 1 chunk, the first mapping, made every load instruction touch 32 lines: the L1 tag stage
-//    ran at 84 % of its peak and bounded the loop, ncu profiles/r02t.)
-//  - rows contiguous in memory (the transposed operands of the backward GEMMs): a warp = 32 rows x 1 chunk, whose four
-//    scalar loads are one line each.
+
+// which 16-byte chunk (row r, K chunk kc) of a block thread c moves.  Shared memory holds a block K-major in the 128-byte
+// swizzle the tensor core reads natively (UMMA layout type SWIZZLE_128B): row r is one 128-byte line (GK = 32 floats), its
+// chunk kc at r * 128 + ((kc ^ (r % 8)) * 16); eight-row groups are 1024 bytes apart.
+//  - K contiguous in memory (row-major operand): a quarter warp = the 8 chunks of one row: one whole 128-byte line from
+//    global memory (a 16-byte load is processed a quarter warp at a time: the earlier layouts -- 32 rows x 1 chunk, then
+//    8 rows x 4 chunks per warp -- cost 32 data-pipe wavefronts per load instruction either way, and the L1 data pipe
+//    at 67-81 % of its peak bounded the loop, ncu profiles/r02t, r02w), and one whole line of shared memory, conflict-free.
+//  - rows contiguous in memory (the transposed operands of the backward GEMMs): a warp = 32 rows x 1 chunk: its four
+//    scalar loads are one line each, and the swizzle spreads a quarter warp's eight rows over all banks.
+// (The first version had consecutive threads on consecutive chunks of a row in the unswizzled layout: 87 % of its
+// shared-memory wavefronts were bank conflicts, ncu profiles/r02h.)
 template <int ROWS>
 __device__ __forceinline__ void g_chunk(int c, bool k_contig, int& r, int& kc) {
     if (k_contig) {
-        const int lane = c & 31, w = c >> 5;                  // warp-sized group w: rows 8 (w % (ROWS/8)) .., chunks 4 (w / (ROWS/8)) ..
-        r = 8 * (w % (ROWS / 8)) + (lane & 7);
-        kc = 4 * (w / (ROWS / 8)) + (lane >> 3);
+        r = c >> 3;
+        kc = c & 7;
     } else {
         r = c % ROWS;
         kc = c / ROWS;
     }
 }
-template <int ROWS>
-struct GFrag { float4 v[ROWS * (GK / 4) / G_THREADS]; };
-template <int ROWS>
-__device__ __forceinline__ void g_load(GFrag<ROWS>& f, const float* __restrict__ src, long long s_row, long long s_k, int row0,
-                                       int nrows, int k0, int K, int tid) {
-    static_assert(ROWS * (GK / 4) % G_THREADS == 0, "whole chunks per thread");
-#pragma unroll
-    for (int i = 0; i < ROWS * (GK / 4) / G_THREADS; ++i) {
+// one thread's view of an operand: where its chunk of the next K block is, set up once per CTA
+struct GLoader {
+    const float* p;                                   // element (row, k) of the next block's chunk
+    long long s_k, step;                              // element stride along K; advance per K block
+    int k;                                            // its K index (bounds only matter in a ragged last block)
+    uint32_t off;                                     // byte offset of the chunk inside a staged block
+    bool row_ok, vec;                                 // row inside the matrix; one aligned 16-byte load per chunk
+    template <int ROWS>
+    __device__ __forceinline__ void init(const float* src, long long s_row, long long sk, int row0, int nrows, int k0, int tid) {
         int r, kc;
-        g_chunk<ROWS>(tid + i * G_THREADS, s_k == 1, r, kc);
+        g_chunk<ROWS>(tid, sk == 1, r, kc);
+        const int row = row0 + r;
+        row_ok = row < nrows;
+        k = k0 + 4 * kc;
+        s_k = sk;
+        step = (long long)GK * sk;
+        p = src + (long long)(row_ok ? row : 0) * s_row + (long long)k * sk;
+        vec = sk == 1 && (reinterpret_cast<uintptr_t>(p) & 15) == 0;       // a K block is 128 bytes: alignment holds for all
+        off = (uint32_t)(r * 128 + ((kc ^ (r & 7)) << 4));
+    }
+    __device__ __forceinline__ float4 load(int K) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int row = row0 + r, k = k0 + 4 * kc;
-        if (row < nrows) {
-            const float* p = src + (long long)row * s_row + (long long)k * s_k;
-            if (s_k == 1 && k + 3 < K && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) v = __ldg(reinterpret_cast<const float4*>(p));
+        if (row_ok) {
+            if (vec && k + 3 < K) v = __ldg(reinterpret_cast<const float4*>(p));
             else {
                 if (k < K) v.x = __ldg(p);
                 if (k + 1 < K) v.y = __ldg(p + s_k);
@@ -150,38 +173,43 @@ __device__ __forceinline__ void g_load(GFrag<ROWS>& f, const float* __restrict__
                 if (k + 3 < K) v.w = __ldg(p + 3 * s_k);
             }
         }
-        f.v[i] = v;
+        p += step;
+        k += GK;
+        return v;
     }
-}
-template <int ROWS>
-__device__ __forceinline__ void g_split(unsigned char* hi, unsigned char* lo, const GFrag<ROWS>& f, bool k_contig, int tid) {
-#pragma unroll
-    for (int i = 0; i < ROWS * (GK / 4) / G_THREADS; ++i) {
-        int r, kc;
-        g_chunk<ROWS>(tid + i * G_THREADS, k_contig, r, kc);
-        const float4 v = f.v[i];
-        const float4 h = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
-        const float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);       // exact
-        const int off = kc * (ROWS * 16) + r * 16;
+    __device__ __forceinline__ void split(unsigned char* hi, unsigned char* lo, const float4 v) const {
+        float4 h, l;
+        tf32_split(v.x, h.x, l.x);
+        tf32_split(v.y, h.y, l.y);
+        tf32_split(v.z, h.z, l.z);
+        tf32_split(v.w, h.w, l.w);
         *reinterpret_cast<float4*>(hi + off) = h;
         *reinterpret_cast<float4*>(lo + off) = l;
     }
-}
+};
 
+// Pipeline.  No CTA-wide barrier inside the K loop (the first versions had one per K block, and the slowest of the 32
+// warps' global loads paced every block: 27 % of the stall samples at the barrier, 16 % at the loads, ncu profiles/r02w):
+//   every warp:  wait free[s] (the MMAs that read stage s are complete) -> split its chunks of block kb into stage s ->
+//                issue the loads of block kb + 2 into registers -> fence.proxy.async -> lane 0 arrives on full[s]
+//   warp 0 then: lane 0 waits full[s] (all 32 warps have arrived), issues the block's 12 MMAs and commits them to free[s].
+// Warps other than 0 run up to G_STAGES blocks ahead of the tensor core.
 template <int EPI>
 __global__ void __launch_bounds__(G_THREADS, 1) vr_gemm_tf32x3_kernel(const __grid_constant__ GemmParams p) {
     extern __shared__ __align__(1024) unsigned char gsm[];
-    __shared__ uint64_t bar_free[2], bar_done;
+    __shared__ uint64_t bar_full[G_STAGES], bar_free[G_STAGES], bar_done;
     __shared__ uint32_t tmem_base_s;
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ntn = (p.N + GN - 1) / GN;                         // column tiles fastest: the CTAs that share an A tile run together
     const int tile_n = blockIdx.x % ntn, tile_m = blockIdx.x / ntn;    // (A once from HBM; it was read once per column tile, ncu r02s)
     const int m0 = tile_m * GM, n0 = tile_n * GN;
 
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i)
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&bar_free[i])) : "memory");
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&bar_done)) : "memory");
+        for (int i = 0; i < G_STAGES; ++i) {
+            g_mbar_init(&bar_full[i], G_WARPS);
+            g_mbar_init(&bar_free[i], 1);
+        }
+        g_mbar_init(&bar_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {                                              // one warp allocates (and later frees) the accumulators' 512 columns
@@ -189,6 +217,17 @@ __global__ void __launch_bounds__(G_THREADS, 1) vr_gemm_tf32x3_kernel(const __gr
                      ::"r"((uint32_t)__cvta_generic_to_shared(&tmem_base_s)), "r"((uint32_t)(G_ACC * GN)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    // this thread's chunks, and the first two blocks' loads, before the set-up barrier
+    const int KB_all = (p.K + GK - 1) / GK;
+    const int kb_first = blockIdx.z * p.kb_per_split;
+    const int KB = (KB_all - kb_first < p.kb_per_split) ? (KB_all - kb_first) : p.kb_per_split;     // this slice's K blocks (>= 1)
+    GLoader la, lb;
+    la.init<GM>(p.A, p.sAm, p.sAk, m0, p.M, kb_first * GK, tid);
+    lb.init<GN>(p.B, p.sBn, p.sBk, n0, p.N, kb_first * GK, tid);
+    float4 fa0 = la.load(p.K), fb0 = lb.load(p.K);
+    float4 fa1 = make_float4(0.f, 0.f, 0.f, 0.f), fb1 = fa1;
+    if (KB > 1) { fa1 = la.load(p.K); fb1 = lb.load(p.K); }
+
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -197,54 +236,45 @@ __global__ void __launch_bounds__(G_THREADS, 1) vr_gemm_tf32x3_kernel(const __gr
     // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 [4,6), A = B = TF32 [7,10) [10,13), both K-major,
     // N >> 3 at [17,23), M >> 4 at [24,29)
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(GN >> 3) << 17) | ((uint32_t)(GM >> 4) << 24);
-    const int KB_all = (p.K + GK - 1) / GK;
-    const int kb_first = blockIdx.z * p.kb_per_split;
-    const int KB = (KB_all - kb_first < p.kb_per_split) ? (KB_all - kb_first) : p.kb_per_split;     // this slice's K blocks
-    GFrag<GM> fa[2];
-    GFrag<GN> fb[2];
-    const int k_first = kb_first * GK;
-    g_load<GM>(fa[0], p.A, p.sAm, p.sAk, m0, p.M, k_first, p.K, tid);
-    g_load<GN>(fb[0], p.B, p.sBn, p.sBk, n0, p.N, k_first, p.K, tid);
-    if (KB > 1) {
-        g_load<GM>(fa[1], p.A, p.sAm, p.sAk, m0, p.M, k_first + GK, p.K, tid);
-        g_load<GN>(fb[1], p.B, p.sBn, p.sBk, n0, p.N, k_first + GK, p.K, tid);
-    }
-    auto k_block = [&](const int kb, GFrag<GM>& ra, GFrag<GN>& rb) {
-        const int s = kb & 1;
+    int s = 0;                                                    // stage of block kb, and how often it has been used before
+    uint32_t use = 0;
+    auto k_block = [&](const int kb, float4& ra, float4& rb) {
         unsigned char* st = gsm + s * G_STAGE_BYTES;
         unsigned char* a_hi = st, *a_lo = st + GM * GK * 4, *b_hi = st + 2 * GM * GK * 4, *b_lo = b_hi + GN * GK * 4;
-        if (kb >= 2) g_mbar_wait(&bar_free[s], (uint32_t)(((kb >> 1) - 1) & 1));    // the MMAs that read this stage have completed
-        g_split<GM>(a_hi, a_lo, ra, p.sAk == 1, tid);
-        g_split<GN>(b_hi, b_lo, rb, p.sBk == 1, tid);
-        if (kb + 2 < KB) {                                        // the block after next: in flight over two barriers
-            g_load<GM>(ra, p.A, p.sAm, p.sAk, m0, p.M, k_first + (kb + 2) * GK, p.K, tid);
-            g_load<GN>(rb, p.B, p.sBn, p.sBk, n0, p.N, k_first + (kb + 2) * GK, p.K, tid);
-        }
+        if (use > 0) g_mbar_wait(&bar_free[s], (use - 1) & 1);    // the MMAs that read this stage have completed
+        la.split(a_hi, a_lo, ra);
+        lb.split(b_hi, b_lo, rb);
+        if (kb + 2 < KB) { ra = la.load(p.K); rb = lb.load(p.K); }       // the block after next: in flight over two blocks
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the tensor core's reads
-        __syncthreads();
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t ah = (uint32_t)__cvta_generic_to_shared(a_hi), al = (uint32_t)__cvta_generic_to_shared(a_lo);
-            const uint32_t bh = (uint32_t)__cvta_generic_to_shared(b_hi), bl = (uint32_t)__cvta_generic_to_shared(b_lo);
+        __syncwarp();
+        if (lane == 0) g_mbar_arrive(&bar_full[s]);
+        if (warp == 0) {
+            if (lane == 0) {
+                g_mbar_wait(&bar_full[s], use & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t ah = (uint32_t)__cvta_generic_to_shared(a_hi), al = (uint32_t)__cvta_generic_to_shared(a_lo);
+                const uint32_t bh = (uint32_t)__cvta_generic_to_shared(b_hi), bl = (uint32_t)__cvta_generic_to_shared(b_lo);
 #pragma unroll
-            for (int ks = 0; ks < GK / 8; ++ks) {                 // K = 8 per instruction = two 16-byte chunks
-                const uint32_t ao = ks * 2 * (GM * 16), bo = ks * 2 * (GN * 16);
-                const uint64_t dah = umma_desc_kmajor(ah + ao, GM * 16, 128), dal = umma_desc_kmajor(al + ao, GM * 16, 128);
-                const uint64_t dbh = umma_desc_kmajor(bh + bo, GN * 16, 128), dbl = umma_desc_kmajor(bl + bo, GN * 16, 128);
-                const int step = kb * (GK / 8) + ks, big = step % (G_ACC - 1);
-                umma_tf32(tmem + big * GN, dah, dbh, idesc, step >= G_ACC - 1 ? 1u : 0u);       // hi.hi: rotate over three accumulators
-                umma_tf32(tmem + (G_ACC - 1) * GN, dal, dbh, idesc, step > 0 ? 1u : 0u);        // the small cross terms: the fourth
-                umma_tf32(tmem + (G_ACC - 1) * GN, dah, dbl, idesc, 1u);
+                for (int ks = 0; ks < GK / 8; ++ks) {             // K = 8 per instruction = 32 bytes of every row
+                    const uint64_t dah = umma_desc_kmajor_sw128(ah + ks * 32), dal = umma_desc_kmajor_sw128(al + ks * 32);
+                    const uint64_t dbh = umma_desc_kmajor_sw128(bh + ks * 32), dbl = umma_desc_kmajor_sw128(bl + ks * 32);
+                    const int step = kb * (GK / 8) + ks, big = step % (G_ACC - 1);
+                    umma_tf32(tmem + big * GN, dah, dbh, idesc, step >= G_ACC - 1 ? 1u : 0u);   // hi.hi: rotate over three accumulators
+                    umma_tf32(tmem + (G_ACC - 1) * GN, dal, dbh, idesc, step > 0 ? 1u : 0u);    // the small cross terms: the fourth
+                    umma_tf32(tmem + (G_ACC - 1) * GN, dah, dbl, idesc, 1u);
+                }
+                umma_commit(&bar_free[s]);                        // arrives when the MMAs issued so far have read shared memory
+                if (kb == KB - 1) umma_commit(&bar_done);
             }
-            umma_commit(&bar_free[s]);                            // arrives when the MMAs issued so far have read shared memory
-            if (kb == KB - 1) umma_commit(&bar_done);
+            __syncwarp();
         }
+        if (++s == G_STAGES) { s = 0; ++use; }
     };
     for (int kb = 0; kb < KB; kb += 2) {
-        k_block(kb, fa[0], fb[0]);
-        if (kb + 1 < KB) k_block(kb + 1, fa[1], fb[1]);
+        k_block(kb, fa0, fb0);
+        if (kb + 1 < KB) k_block(kb + 1, fa1, fb1);
     }
-    g_mbar_wait(&bar_done, 0u);
+    if (KB > 0) g_mbar_wait(&bar_done, 0u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
     // ---- epilogue: thread = accumulator row (TMEM lane 32 * (warp % 4) + lane); the warps of each group of four take one
@@ -252,43 +282,46 @@ __global__ void __launch_bounds__(G_THREADS, 1) vr_gemm_tf32x3_kernel(const __gr
     const int m = m0 + (tid & 127);
     const int part = warp >> 2;
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    const int steps = KB * (GK / 8), nbig = steps < G_ACC - 1 ? steps : G_ACC - 1;     // big accumulators that hold data
     if (EPI == 0) {
-        for (int c0 = part * (GN / G_PARTS); c0 < (part + 1) * (GN / G_PARTS); c0 += 16) {
-            float v[16];
-            tmem_ld16_sum(trow + c0, nbig, v);
-            if (m < p.M) {
+        constexpr int W = GN / G_PARTS;                           // 16 columns per thread
+        float v[W];
+        const int c0 = part * W;
+        if (KB > 0) tmem_ld_sum<W>(trow + c0, v);
+        if (KB > 0 && m < p.M) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (n0 + c0 + j < p.N) {
-                        float* dst = p.C + (long long)m * p.ldc + n0 + c0 + j;
-                        if (gridDim.z > 1) atomicAdd(dst, v[j]);        // split K: C was zeroed by the host
-                        else *dst = v[j];
-                    }
-            }
+            for (int j = 0; j < W; ++j)
+                if (n0 + c0 + j < p.N) {
+                    float* dst = p.C + (long long)m * p.ldc + n0 + c0 + j;
+                    if (gridDim.z > 1) atomicAdd(dst, v[j]);      // split K: C was zeroed by the host
+                    else *dst = v[j];
+                }
         }
     } else {
         // column tile: [re of bins t*nb .. | im of the same bins]; out[(seq * n_fft + ((bin + n_fft/2) % n_fft)) * F + f]
-        const int nb = p.nb, tile = tile_n;
+        constexpr int W = 8;
+        const int nb = p.nb;                                      // a power of two >= 16
+        const int parts = nb / W < G_PARTS ? nb / W : G_PARTS;
+        const int per = nb / parts;                               // bins per part: a multiple of 8
         const int seq = m / p.F, f = m - seq * p.F;
-        const int parts = (nb / 16 < G_PARTS) ? (nb / 16 > 0 ? nb / 16 : 1) : G_PARTS;      // 16-column loads: every part a multiple of 16 bins
-        const int per = (nb / parts + 15) / 16 * 16;
-        const int cb = part < parts ? part * per : 0, ce = part < parts ? (cb + per < nb ? cb + per : nb) : 0;
-        for (int c0 = cb; c0 < ce; c0 += 16) {
-            float re[16], im[16];
-            tmem_ld16_sum(trow + c0, nbig, re);
-            tmem_ld16_sum(trow + nb + c0, nbig, im);
-            if (m < p.M) {
+        if (part < parts) {
+            for (int c0 = part * per; c0 < (part + 1) * per; c0 += W) {
+                float re[W], im[W];
+                tmem_ld_sum<W>(trow + c0, re);
+                tmem_ld_sum<W>(trow + nb + c0, im);
+                if (m < p.M) {
+                    float* o = p.out + (long long)seq * p.n_fft * p.F + f;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int bin = tile * nb + c0 + j;
-                    if (c0 + j < nb && bin < p.n_fft) {
-                        const float mag = sqrtf(fmaf(re[j], re[j], im[j] * im[j]));
-                        const int row = (bin + p.n_fft / 2) % p.n_fft;
-                        p.out[((long long)seq * p.n_fft + row) * p.F + f] = logf(mag + 1e-6f);
-                        if (p.csave) {
-                            p.csave[(long long)(n0 + c0 + j) * p.ldc + m] = re[j];          // column-major: lanes = rows, coalesced
-                            p.csave[(long long)(n0 + nb + c0 + j) * p.ldc + m] = im[j];
+                    for (int j = 0; j < W; ++j) {
+                        const int bin = tile_n * nb + c0 + j;
+                        if (bin < p.n_fft) {
+                            const float mag = sqrtf(fmaf(re[j], re[j], im[j] * im[j]));
+                            int row = bin + (p.n_fft >> 1);
+                            row = row >= p.n_fft ? row - p.n_fft : row;
+                            o[(long long)row * p.F] = logf(mag + 1e-6f);
+                            if (p.csave) {
+                                p.csave[(long long)(n0 + c0 + j) * p.ldc + m] = re[j];          // column-major: lanes = rows, coalesced
+                                p.csave[(long long)(n0 + nb + c0 + j) * p.ldc + m] = im[j];
+                            }
                         }
                     }
                 }
