@@ -172,7 +172,8 @@ int vr_backward_params_f32(const float* x_dev, const float* iq_dev, const float*
  * tensor cores (tcgen05.mma kind::tf32 with the error-compensated 3-term split, accumulator in tensor memory) whose
  * epilogue takes the magnitude, the log and the fftshift roll.  Any power-of-two n_fft in [16, 1024].
  *   iq_dev (N, T, 2): the complex baseband signal (vr_forward_debug_f32's iq_dev);  wsin_dev / wcos_dev (n_fft, 1, n_fft);
- *   out_dev (N, n_fft, T/hop + 1).  Work buffers (sizes from vr_stft_general_workspace_floats: parts[0] frames,
+ *   out_dev (N, n_fft, T/hop + 1).  Work buffers (sizes from vr_stft_general_workspace_floats: parts[0] the
+ *   reflect-padded planar signal -- the frame matrix is never materialised, the GEMM reads the frames as views of it --
  *   parts[1] kernel matrix, parts[2] saved Re/Im): frames_work and bt_work are scratch that the backward pass re-reads;
  *   c_save (optional, NULL = inference) keeps Re / Im of every bin for it.                                          */
 int64_t vr_stft_general_workspace_floats(int64_t N, int64_t T, int32_t n_fft, int32_t hop, int64_t parts[3]);
@@ -181,7 +182,8 @@ int vr_stft_general_f32(const float* iq_dev, int64_t N, int64_t T, int32_t n_fft
                         float* c_save, float* out_dev, void* stream);
 /* Its backward pass (the reference differentiates the conv1d graph with autograd): from dL/d(out) and the three buffers of
  * the forward to dL/d(iq) (N, T, 2) -- feed it to vr_synth_adjoint_f32 -- and dL/d(wsin), dL/d(wcos) (n_fft, 1, n_fft).
- * Two more GEMMs on the same kernel (dA = dC . Bt, dBt = dC^T . A).  dc_work: parts[2] floats; da_work: parts[0] floats
+ * Two more GEMMs on the same kernel (dA = dC . Bt, dBt = dC^T . A).  dc_work: parts[2] floats; da_work: the frame
+ * gradients, N * (T/hop + 1) * 2 * n_fft floats
  * (NULL together with grad_iq_dev when x and the radar parameters need no gradient); dbt_work: parts[1] floats (NULL
  * together with grad_wsin_dev / grad_wcos_dev when the kernels are frozen).                                         */
 int vr_stft_general_backward_f32(const float* grad_out_dev, const float* frames_work, const float* bt_work, const float* c_save,

@@ -935,8 +935,9 @@ int gemm_setup(int dev) {
     static bool done[64] = {false};
     std::lock_guard<std::mutex> lk(mu);
     if (!done[dev]) {
-        CUDA_TRY(cudaFuncSetAttribute(vr::vr_gemm_tf32x3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, vr::G_SMEM_BYTES));
-        CUDA_TRY(cudaFuncSetAttribute(vr::vr_gemm_tf32x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, vr::G_SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(vr::vr_gemm_tf32x3_kernel<1, vr::G_FRAME_ROWS, vr::G_STRIDED>, cudaFuncAttributeMaxDynamicSharedMemorySize, vr::G_SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(vr::vr_gemm_tf32x3_kernel<0, vr::G_STRIDED, vr::G_STRIDED>, cudaFuncAttributeMaxDynamicSharedMemorySize, vr::G_SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(vr::vr_gemm_tf32x3_kernel<0, vr::G_STRIDED, vr::G_FRAME_COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, vr::G_SMEM_BYTES));
         done[dev] = true;
     }
     return VR_OK;
@@ -954,11 +955,12 @@ int stft_check(int64_t N, int64_t T, int n_fft, int hop) {
 extern "C" {
 
 static long long stft_ldm(long long M) { return (M + 3) & ~3ll; }
+static long long stft_lp(long long T, int n_fft) { return (T + n_fft + 3) & ~3ll; }     // padded signal length, 16-byte rows
 
 int64_t vr_stft_general_workspace_floats(int64_t N, int64_t T, int32_t n_fft, int32_t hop, int64_t parts[3]) {
     if (N <= 0 || T <= 0 || hop <= 0 || n_fft <= 0) return 0;
     const int64_t M = N * (T / hop + 1), K = 2ll * n_fft;
-    const int64_t a = M * K, b = K * K, c = K * stft_ldm(M);       // C / dC: column-major, leading dimension a multiple of 4
+    const int64_t a = 2 * N * stft_lp(T, n_fft), b = K * K, c = K * stft_ldm(M);   // padded planar signal (the frames are views of it);       // C / dC: column-major, leading dimension a multiple of 4
     if (parts) { parts[0] = a; parts[1] = b; parts[2] = c; }
     return a + b + c;
 }
@@ -977,16 +979,17 @@ int vr_stft_general_f32(const float* iq_dev, int64_t N, int64_t T, int32_t n_fft
     cudaStream_t st = (cudaStream_t)stream;
     const int F = (int)(T / hop) + 1, nb = stft_nb(n_fft), K = 2 * n_fft;
     const long long M = N * (long long)F;
-    vr::vr_stft_frames_kernel<<<(unsigned)std::min<long long>((M * n_fft + 255) / 256, sm_count * 16ll), 256, 0, st>>>(iq_dev, frames_work, N, (int)T, F, n_fft, hop);
+    const long long Lp = stft_lp(T, n_fft);
+    vr::vr_stft_pad_kernel<<<(unsigned)std::min<long long>((N * Lp + 255) / 256, sm_count * 16ll), 256, 0, st>>>(iq_dev, frames_work, N, (int)T, Lp, n_fft);
     vr::vr_stft_bt_kernel<<<(n_fft * n_fft + 255) / 256, 256, 0, st>>>(wsin_dev, wcos_dev, bt_work, n_fft, nb);
     vr::GemmParams g;
     memset(&g, 0, sizeof(g));
-    g.A = frames_work; g.sAm = K; g.sAk = 1;
+    g.P = frames_work; g.Lp = Lp; g.hop = hop;       // A = the frames, read as views of the padded signal
     g.B = bt_work; g.sBn = K; g.sBk = 1;
     g.M = (int)M; g.N = K; g.K = K; g.kb_per_split = (K + vr::GK - 1) / vr::GK;
     g.out = out_dev; g.csave = c_save; g.ldc = stft_ldm(M); g.F = F; g.n_fft = n_fft; g.nb = nb;
     dim3 grid((unsigned)(((M + vr::GM - 1) / vr::GM) * ((K + vr::GN - 1) / vr::GN)));
-    vr::vr_gemm_tf32x3_kernel<1><<<grid, vr::G_THREADS, vr::G_SMEM_BYTES, st>>>(g);
+    vr::vr_gemm_tf32x3_kernel<1, vr::G_FRAME_ROWS, vr::G_STRIDED><<<grid, vr::G_THREADS, vr::G_SMEM_BYTES, st>>>(g);
     CUDA_TRY(cudaGetLastError());
     return VR_OK;
 }
@@ -1009,9 +1012,8 @@ int vr_stft_general_backward_f32(const float* grad_out_dev, const float* frames_
     cudaStream_t st = (cudaStream_t)stream;
     const int F = (int)(T / hop) + 1, nb = stft_nb(n_fft), K = 2 * n_fft;
     const long long M = N * (long long)F;
-    const unsigned eb = (unsigned)std::min<long long>((M * n_fft + 255) / 256, sm_count * 16ll);
     const long long ldm = stft_ldm(M);
-    vr::vr_stft_dc_kernel<<<eb, 256, 0, st>>>(grad_out_dev, c_save, dc_work, M, ldm, F, n_fft, nb);
+    vr::vr_stft_dc_kernel<<<dim3((unsigned)std::min<long long>((M / 4 + 256) / 256, sm_count * 4ll), (unsigned)n_fft), 256, 0, st>>>(grad_out_dev, c_save, dc_work, (int)M, ldm, F, n_fft, nb);
     vr::GemmParams g;
     if (da_work) {                                   // dA[m, k] = sum_n dC[m, n] Bt[n, k]
         memset(&g, 0, sizeof(g));
@@ -1019,25 +1021,26 @@ int vr_stft_general_backward_f32(const float* grad_out_dev, const float* frames_
         g.B = bt_work; g.sBn = 1; g.sBk = K;         // B'(n' = k, k' = n) = Bt[n][k]
         g.M = (int)M; g.N = K; g.K = K; g.C = da_work; g.ldc = K; g.kb_per_split = (K + vr::GK - 1) / vr::GK;
         dim3 grid((unsigned)(((M + vr::GM - 1) / vr::GM) * ((K + vr::GN - 1) / vr::GN)));
-        vr::vr_gemm_tf32x3_kernel<0><<<grid, vr::G_THREADS, vr::G_SMEM_BYTES, st>>>(g);
-        CUDA_TRY(cudaMemsetAsync(grad_iq_dev, 0, (size_t)N * T * 2 * sizeof(float), st));
-        vr::vr_stft_fold_kernel<<<eb, 256, 0, st>>>(da_work, grad_iq_dev, N, (int)T, F, n_fft, hop);
+        vr::vr_gemm_tf32x3_kernel<0, vr::G_STRIDED, vr::G_STRIDED><<<grid, vr::G_THREADS, vr::G_SMEM_BYTES, st>>>(g);
+        vr::vr_stft_fold_kernel<<<(unsigned)std::min<long long>((N * T + 255) / 256, sm_count * 16ll), 256, 0, st>>>(da_work, grad_iq_dev, N, (int)T, F, n_fft, hop);
     }
     if (dbt_work) {                                  // dBt[n, k] = sum_m dC[m, n] A[m, k]
         memset(&g, 0, sizeof(g));
         g.A = dc_work; g.sAm = ldm; g.sAk = 1;       // A'(m' = n, k' = m) = dC(m, n) = dc[n * ldm + m]: rows of 16-byte aligned chunks
-        g.B = frames_work; g.sBn = 1; g.sBk = K;     // B'(n' = k, k' = m) = A[m][k]
+        g.P = frames_work; g.Lp = stft_lp(T, n_fft); g.hop = hop; g.F = F; g.n_fft = n_fft;     // B'(n' = k, k' = m) = A[m][k], a view
         g.M = K; g.N = K; g.K = (int)M; g.C = dbt_work; g.ldc = K;
         // the reduction runs over all frames of the batch: split it over gridDim.z so that the (2 n_fft / 128)^2 output
         // tiles fill the machine; the slices add into the zeroed result with float atomics
         const int tiles = ((K + vr::GM - 1) / vr::GM) * ((K + vr::GN - 1) / vr::GN);
         const int kb_all = (int)((M + vr::GK - 1) / vr::GK);
-        int splits = std::max(1, std::min((2 * sm_count + tiles - 1) / tiles, (kb_all + 7) / 8));
+        // one CTA per SM at a time (192 KB of stages): whole waves, i.e. splits * tiles <= a multiple of sm_count; one wave
+        // unless that leaves a slice fewer than 8 K blocks
+        int splits = std::max(1, std::min(sm_count / tiles, (kb_all + 7) / 8));
         g.kb_per_split = (kb_all + splits - 1) / splits;
         splits = (kb_all + g.kb_per_split - 1) / g.kb_per_split;
         if (splits > 1) CUDA_TRY(cudaMemsetAsync(dbt_work, 0, (size_t)K * K * sizeof(float), st));
         dim3 grid((unsigned)(((K + vr::GM - 1) / vr::GM) * ((K + vr::GN - 1) / vr::GN)), 1u, (unsigned)splits);
-        vr::vr_gemm_tf32x3_kernel<0><<<grid, vr::G_THREADS, vr::G_SMEM_BYTES, st>>>(g);
+        vr::vr_gemm_tf32x3_kernel<0, vr::G_STRIDED, vr::G_FRAME_COLS><<<grid, vr::G_THREADS, vr::G_SMEM_BYTES, st>>>(g);
         vr::vr_stft_dw_kernel<<<(n_fft * n_fft + 255) / 256, 256, 0, st>>>(dbt_work, grad_wsin_dev, grad_wcos_dev, n_fft, nb);
     }
     CUDA_TRY(cudaGetLastError());

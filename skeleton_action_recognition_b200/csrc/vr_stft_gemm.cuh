@@ -32,6 +32,15 @@
 
 namespace vr {
 
+// A/B switches of the operand loads (tools/ab.py build + tools/ab_stft.py, profiles/r02z7_ab_stft.log): PTX-predicated
+// loads pay for the frame-column view (backward 1.271 -> 1.119 ms at 4096 sequences) and cost the strided loader
+// (forward 0.474 -> 0.529 ms), so each loader keeps the form that measured faster.
+#ifndef VR_GEMM_ASM_STRIDED
+#define VR_GEMM_ASM_STRIDED 0
+#endif
+#ifndef VR_GEMM_ASM_COLS
+#define VR_GEMM_ASM_COLS 1
+#endif
 constexpr int GM = 128, GN = 128, GK = 32;          // CTA tile, K block per stage
 constexpr int G_THREADS = 1024;                     // every thread stages one 16-byte chunk of A and one of B per K block;
 constexpr int G_WARPS = G_THREADS / 32;             // warp w reads accumulator lanes 32 (w % 4) and the (w / 4)-th part of
@@ -52,7 +61,11 @@ struct GemmParams {
     float* C; long long ldc;                        // EPI 0: C[m * ldc + n]
     float* out; float* csave;                       // EPI 1: (sequences, n_fft, F) log-magnitude; optional raw C, column-major (N x ldc)
     int F, n_fft, nb;                               // frames per sequence; bins per column tile (re block | im block)
+    // the frame matrix as a VIEW of the padded signal (operand modes 1 and 2): frame row m = (sequence s, frame f),
+    // column k = (component c = k / n_fft, sample j = k % n_fft)  ->  P[(s * 2 + c) * Lp + f * hop + j]
+    const float* P; long long Lp; int hop;
 };
+enum { G_STRIDED = 0, G_FRAME_ROWS = 1, G_FRAME_COLS = 2 };
 
 #ifdef __CUDACC__
 __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t saddr) {
@@ -142,15 +155,45 @@ __device__ __forceinline__ void g_chunk(int c, bool k_contig, int& r, int& kc) {
         kc = c / ROWS;
     }
 }
-// one thread's view of an operand: where its chunk of the next K block is, set up once per CTA
-struct GLoader {
+// one thread's view of an operand: where its chunk of the next K block is, set up once per CTA.
+//   G_STRIDED     X(row, k) = src[row * s_row + k * s_k]
+//   G_FRAME_ROWS  X(m, k)   = frame m, column k of the padded signal (the forward's A): nothing is materialised, the 16-fold
+//                 overlap of the frames is read from L2 instead of being written to and read back from HBM
+//   G_FRAME_COLS  X(k, m)   = the same matrix transposed (B of the kernel-gradient GEMM: its K index runs over the frames)
+// Predicated loads, written as PTX so that the value has ONE definition: with `v = 0; if (ok) v = load` the compiler may copy
+// the loaded registers into the merged variable right behind the load, i.e. wait for it there -- in the kernel-gradient
+// GEMM the loads meant to be in flight over two K blocks were not (22 % of the stall samples sat on those copies, ncu
+// profiles/r02z4).  Used where it measured faster (see VR_GEMM_ASM_*).
+__device__ __forceinline__ float4 ldg_v4_if(const float* q, bool ok) {
+    float4 v;
+    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %5, 0;\n mov.f32 %0, 0f00000000;\n mov.f32 %1, 0f00000000;\n mov.f32 %2, 0f00000000;\n"
+                 " mov.f32 %3, 0f00000000;\n @p ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n}"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(q), "r"((int)ok));
+    return v;
+}
+__device__ __forceinline__ void ldg_into_if(float& v, const float* q, bool ok) {      // v keeps its value when !ok
+    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %2, 0;\n @p ld.global.nc.f32 %0, [%1];\n}" : "+f"(v) : "l"(q), "r"((int)ok));
+}
+__device__ __forceinline__ void tf32_store_split(unsigned char* hi, unsigned char* lo, uint32_t off, const float4 v) {
+    float4 h, l;
+    tf32_split(v.x, h.x, l.x);
+    tf32_split(v.y, h.y, l.y);
+    tf32_split(v.z, h.z, l.z);
+    tf32_split(v.w, h.w, l.w);
+    *reinterpret_cast<float4*>(hi + off) = h;
+    *reinterpret_cast<float4*>(lo + off) = l;
+}
+template <int MODE>
+struct GLoader;
+template <>
+struct GLoader<G_STRIDED> {
     const float* p;                                   // element (row, k) of the next block's chunk
     long long s_k, step;                              // element stride along K; advance per K block
     int k;                                            // its K index (bounds only matter in a ragged last block)
     uint32_t off;                                     // byte offset of the chunk inside a staged block
     bool row_ok, vec;                                 // row inside the matrix; one aligned 16-byte load per chunk
     template <int ROWS>
-    __device__ __forceinline__ void init(const float* src, long long s_row, long long sk, int row0, int nrows, int k0, int tid) {
+    __device__ __forceinline__ void init(const GemmParams&, const float* src, long long s_row, long long sk, int row0, int nrows, int k0, int tid) {
         int r, kc;
         g_chunk<ROWS>(tid, sk == 1, r, kc);
         const int row = row0 + r;
@@ -162,7 +205,15 @@ struct GLoader {
         vec = sk == 1 && (reinterpret_cast<uintptr_t>(p) & 15) == 0;       // a K block is 128 bytes: alignment holds for all
         off = (uint32_t)(r * 128 + ((kc ^ (r & 7)) << 4));
     }
-    __device__ __forceinline__ float4 load(int K) {
+    __device__ __forceinline__ float4 load(const GemmParams&, int K) {
+#if VR_GEMM_ASM_STRIDED
+        const bool whole = row_ok && vec && k + 3 < K, parts = row_ok && !whole;
+        float4 v = ldg_v4_if(p, whole);
+        ldg_into_if(v.x, p, parts && k < K);
+        ldg_into_if(v.y, p + s_k, parts && k + 1 < K);
+        ldg_into_if(v.z, p + 2 * s_k, parts && k + 2 < K);
+        ldg_into_if(v.w, p + 3 * s_k, parts && k + 3 < K);
+#else
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (row_ok) {
             if (vec && k + 3 < K) v = __ldg(reinterpret_cast<const float4*>(p));
@@ -173,18 +224,81 @@ struct GLoader {
                 if (k + 3 < K) v.w = __ldg(p + 3 * s_k);
             }
         }
+#endif
         p += step;
         k += GK;
         return v;
     }
-    __device__ __forceinline__ void split(unsigned char* hi, unsigned char* lo, const float4 v) const {
-        float4 h, l;
-        tf32_split(v.x, h.x, l.x);
-        tf32_split(v.y, h.y, l.y);
-        tf32_split(v.z, h.z, l.z);
-        tf32_split(v.w, h.w, l.w);
-        *reinterpret_cast<float4*>(hi + off) = h;
-        *reinterpret_cast<float4*>(lo + off) = l;
+};
+template <>
+struct GLoader<G_FRAME_ROWS> {
+    const float* base;                                // P + s * 2 Lp + f * hop: sample 0 of the I frame
+    int k;
+    uint32_t off;
+    bool row_ok, vec;
+    template <int ROWS>
+    __device__ __forceinline__ void init(const GemmParams& g, const float*, long long, long long, int row0, int nrows, int k0, int tid) {
+        int r, kc;
+        g_chunk<ROWS>(tid, true, r, kc);
+        const int row = row0 + r;
+        row_ok = row < nrows;
+        k = k0 + 4 * kc;
+        const int m = row_ok ? row : 0, sq = m / g.F, f = m - sq * g.F;
+        base = g.P + (long long)sq * 2 * g.Lp + (long long)f * g.hop;
+        vec = (g.hop & 3) == 0 && (g.Lp & 3) == 0 && (reinterpret_cast<uintptr_t>(g.P) & 15) == 0;      // k, n_fft are multiples of 4
+        off = (uint32_t)(r * 128 + ((kc ^ (r & 7)) << 4));
+    }
+    __device__ __forceinline__ float4 load(const GemmParams& g, int K) {                // K = 2 n_fft, a multiple of 4
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);                                    // (plain loads: the PTX form was slower here, r02z5)
+        if (row_ok && k < K) {
+            const float* q = base + (k >= g.n_fft ? g.Lp - g.n_fft : 0ll) + k;           // the Q frame lives in the next plane
+            if (vec) v = __ldg(reinterpret_cast<const float4*>(q));
+            else v = make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3));
+        }
+        k += GK;
+        return v;
+    }
+};
+template <>
+struct GLoader<G_FRAME_COLS> {
+    const float* q;                                   // this row's sample in frame m
+    int m, f;                                         // frame index of the chunk's first element, and its frame number in its sequence
+    uint32_t off;
+    bool row_ok;
+    template <int ROWS>
+    __device__ __forceinline__ void init(const GemmParams& g, const float*, long long, long long, int row0, int nrows, int k0, int tid) {
+        int r, kc;
+        g_chunk<ROWS>(tid, false, r, kc);
+        const int row = row0 + r;
+        row_ok = row < nrows;
+        const int col = row_ok ? row : 0, c = col >= g.n_fft ? 1 : 0;
+        m = k0 + 4 * kc;
+        const int sq = m / g.F;
+        f = m - sq * g.F;
+        q = g.P + (long long)c * g.Lp + (col - c * g.n_fft) + (long long)sq * 2 * g.Lp + (long long)f * g.hop;
+        off = (uint32_t)(r * 128 + ((kc ^ (r & 7)) << 4));
+    }
+    // the next frame is hop samples further, or -- after a sequence's last frame -- at the start of the next sequence's
+    // planes: a running pointer, no division and no 64-bit multiply per element
+    __device__ __forceinline__ float4 load(const GemmParams& g, int K) {                // K = number of frames
+        const long long wrap = 2 * g.Lp - (long long)g.F * g.hop;                       // uniform: next sequence's frame 0 - (frame F)
+        float e[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#if VR_GEMM_ASM_COLS
+            ldg_into_if(e[j], q, row_ok && m + j < K);
+#else
+            if (row_ok && m + j < K) e[j] = __ldg(q);
+#endif
+            q += g.hop;
+            if (++f == g.F) { f = 0; q += wrap; }
+        }
+        constexpr int REST = GK - 4;                  // to the chunk of the next K block: REST = (REST / F) F + REST % F frames
+        m += GK;
+        f += REST % g.F;
+        q += (long long)(REST / g.F) * 2 * g.Lp + (long long)(REST % g.F) * g.hop;
+        if (f >= g.F) { f -= g.F; q += wrap; }
+        return make_float4(e[0], e[1], e[2], e[3]);
     }
 };
 
@@ -194,7 +308,7 @@ struct GLoader {
 //                issue the loads of block kb + 2 into registers -> fence.proxy.async -> lane 0 arrives on full[s]
 //   warp 0 then: lane 0 waits full[s] (all 32 warps have arrived), issues the block's 12 MMAs and commits them to free[s].
 // Warps other than 0 run up to G_STAGES blocks ahead of the tensor core.
-template <int EPI>
+template <int EPI, int AMODE, int BMODE>
 __global__ void __launch_bounds__(G_THREADS, 1) vr_gemm_tf32x3_kernel(const __grid_constant__ GemmParams p) {
     extern __shared__ __align__(1024) unsigned char gsm[];
     __shared__ uint64_t bar_full[G_STAGES], bar_free[G_STAGES], bar_done;
@@ -221,12 +335,13 @@ __global__ void __launch_bounds__(G_THREADS, 1) vr_gemm_tf32x3_kernel(const __gr
     const int KB_all = (p.K + GK - 1) / GK;
     const int kb_first = blockIdx.z * p.kb_per_split;
     const int KB = (KB_all - kb_first < p.kb_per_split) ? (KB_all - kb_first) : p.kb_per_split;     // this slice's K blocks (>= 1)
-    GLoader la, lb;
-    la.init<GM>(p.A, p.sAm, p.sAk, m0, p.M, kb_first * GK, tid);
-    lb.init<GN>(p.B, p.sBn, p.sBk, n0, p.N, kb_first * GK, tid);
-    float4 fa0 = la.load(p.K), fb0 = lb.load(p.K);
+    GLoader<AMODE> la;
+    GLoader<BMODE> lb;
+    la.template init<GM>(p, p.A, p.sAm, p.sAk, m0, p.M, kb_first * GK, tid);
+    lb.template init<GN>(p, p.B, p.sBn, p.sBk, n0, p.N, kb_first * GK, tid);
+    float4 fa0 = la.load(p, p.K), fb0 = lb.load(p, p.K);
     float4 fa1 = make_float4(0.f, 0.f, 0.f, 0.f), fb1 = fa1;
-    if (KB > 1) { fa1 = la.load(p.K); fb1 = lb.load(p.K); }
+    if (KB > 1) { fa1 = la.load(p, p.K); fb1 = lb.load(p, p.K); }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -242,9 +357,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) vr_gemm_tf32x3_kernel(const __gr
         unsigned char* st = gsm + s * G_STAGE_BYTES;
         unsigned char* a_hi = st, *a_lo = st + GM * GK * 4, *b_hi = st + 2 * GM * GK * 4, *b_lo = b_hi + GN * GK * 4;
         if (use > 0) g_mbar_wait(&bar_free[s], (use - 1) & 1);    // the MMAs that read this stage have completed
-        la.split(a_hi, a_lo, ra);
-        lb.split(b_hi, b_lo, rb);
-        if (kb + 2 < KB) { ra = la.load(p.K); rb = lb.load(p.K); }       // the block after next: in flight over two blocks
+        tf32_store_split(a_hi, a_lo, la.off, ra);
+        tf32_store_split(b_hi, b_lo, lb.off, rb);
+        if (kb + 2 < KB) { ra = la.load(p, p.K); rb = lb.load(p, p.K); }       // the block after next: in flight over two blocks
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the tensor core's reads
         __syncwarp();
         if (lane == 0) g_mbar_arrive(&bar_full[s]);
@@ -283,18 +398,39 @@ __global__ void __launch_bounds__(G_THREADS, 1) vr_gemm_tf32x3_kernel(const __gr
     const int part = warp >> 2;
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     if (EPI == 0) {
+        // the tile goes through shared memory (the stages are free: bar_done covers every MMA) so that global memory sees
+        // whole rows: a thread owns one ROW of the accumulator, and its direct stores were 32 lines per instruction
         constexpr int W = GN / G_PARTS;                           // 16 columns per thread
-        float v[W];
-        const int c0 = part * W;
-        if (KB > 0) tmem_ld_sum<W>(trow + c0, v);
-        if (KB > 0 && m < p.M) {
+        constexpr int LDT = GN + 4;                               // padded row: a quarter warp's 16-byte stores hit all banks
+        static_assert(GM * LDT * 4 <= G_STAGES * G_STAGE_BYTES, "tile fits the stages");
+        float* tile = reinterpret_cast<float*>(gsm);
+        if (KB > 0) {
+            float v[W];
+            tmem_ld_sum<W>(trow + part * W, v);
 #pragma unroll
-            for (int j = 0; j < W; ++j)
-                if (n0 + c0 + j < p.N) {
-                    float* dst = p.C + (long long)m * p.ldc + n0 + c0 + j;
-                    if (gridDim.z > 1) atomicAdd(dst, v[j]);      // split K: C was zeroed by the host
-                    else *dst = v[j];
+            for (int j = 0; j < W; j += 4)
+                *reinterpret_cast<float4*>(tile + (tid & 127) * LDT + part * W + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+        __syncthreads();
+        const bool vec = (p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && gridDim.z == 1;
+        if (KB > 0) {
+            for (int i = tid; i < GM * (GN / 4); i += G_THREADS) {
+                const int r = i / (GN / 4), c = (i % (GN / 4)) * 4;
+                const int gm = m0 + r, gn = n0 + c;
+                if (gm >= p.M || gn >= p.N) continue;
+                const float4 v = *reinterpret_cast<const float4*>(tile + r * LDT + c);
+                float* dst = p.C + (long long)gm * p.ldc + gn;
+                if (vec && gn + 3 < p.N) *reinterpret_cast<float4*>(dst) = v;
+                else {
+                    const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (gn + j < p.N) {
+                            if (gridDim.z > 1) atomicAdd(dst + j, e[j]);      // split K: C was zeroed by the host
+                            else dst[j] = e[j];
+                        }
                 }
+            }
         }
     } else {
         // column tile: [re of bins t*nb .. | im of the same bins]; out[(seq * n_fft + ((bin + n_fft/2) % n_fft)) * F + f]
@@ -334,20 +470,22 @@ __global__ void __launch_bounds__(G_THREADS, 1) vr_gemm_tf32x3_kernel(const __gr
 }
 
 // ---- small kernels around the GEMM -------------------------------------------------------------------------------
-// frames: iq (S, T, 2) -> A (S*F, 2 n_fft): [I frame | Q frame], reflect-padded by n_fft/2 (nnAudio center=True)
-__global__ void vr_stft_frames_kernel(const float* __restrict__ iq, float* __restrict__ A, long long S, int T, int F, int n_fft, int hop) {
-    const long long total = S * F * (long long)n_fft;
+// the padded, planar signal the frame views read: iq (S, T, 2) -> P (S, 2, Lp), P[s][c][j] = iq[s][reflect(j - n_fft/2)][c]
+// for j < T + n_fft (nnAudio center=True, pad_mode='reflect'), 0 beyond.  Frame f of sequence s is P[s][c][f * hop ...].
+__global__ void vr_stft_pad_kernel(const float* __restrict__ iq, float* __restrict__ P, long long S, int T, long long Lp, int n_fft) {
+    const long long total = S * Lp;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int k = (int)(i % n_fft);
-        const long long m = i / n_fft;
-        const int f = (int)(m % F);
-        const long long s = m / F;
-        int t = f * hop - n_fft / 2 + k;
-        t = t < 0 ? -t : t;
-        t = t >= T ? 2 * (T - 1) - t : t;
-        const float2 z = __ldg(reinterpret_cast<const float2*>(iq) + s * T + t);
-        A[m * 2 * n_fft + k] = z.x;
-        A[m * 2 * n_fft + n_fft + k] = z.y;
+        const long long sq = i / Lp;
+        const int j = (int)(i - sq * Lp);
+        float2 z = make_float2(0.f, 0.f);
+        if (j < T + n_fft) {
+            int t = j - n_fft / 2;
+            t = t < 0 ? -t : t;
+            t = t >= T ? 2 * (T - 1) - t : t;
+            z = __ldg(reinterpret_cast<const float2*>(iq) + sq * T + t);
+        }
+        P[sq * 2 * Lp + j] = z.x;
+        P[(sq * 2 + 1) * Lp + j] = z.y;
     }
 }
 // row of Bt that holds Re / Im of `bin` under the column-tile layout [re block | im block] of nb bins
@@ -365,38 +503,72 @@ __global__ void vr_stft_bt_kernel(const float* __restrict__ wsin, const float* _
         im[s] = -sn; im[n_fft + s] = c;
     }
 }
-// backward of ln(|X| + 1e-6) and the roll: dC from grad_out and the saved Re / Im
+// backward of ln(|X| + 1e-6) and the roll: dC from grad_out and the saved Re / Im.  C and dC are column-major (2 n_fft
+// columns of ldm floats, ldm a multiple of 4): blockIdx.y = bin, a thread takes four consecutive rows of its Re and Im
+// columns as 16-byte accesses.
 __global__ void vr_stft_dc_kernel(const float* __restrict__ gout, const float* __restrict__ csave, float* __restrict__ dC,
-                                  long long M, long long ldm, int F, int n_fft, int nb) {
-    // C and dC are column-major (2 n_fft columns of ldm floats): threads run along the rows, every access coalesced
-    const long long total = M * n_fft;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long m = i % M;
-        const int bin = (int)(i / M);
-        const long long seq = m / F;
-        const int f = (int)(m - seq * F);
-        const int cr = stft_row_re(bin, nb), ci = stft_row_im(bin, nb);
-        const float re = csave[cr * ldm + m], im = csave[ci * ldm + m];
-        const float g = __ldg(gout + (seq * n_fft + (bin + n_fft / 2) % n_fft) * F + f);
-        const float mag = sqrtf(fmaf(re, re, im * im));
-        const float w = mag > 0.f ? g / ((mag + 1e-6f) * mag) : 0.f;
-        dC[cr * ldm + m] = w * re;
-        dC[ci * ldm + m] = w * im;
+                                  int M, long long ldm, int F, int n_fft, int nb) {
+    const int bin = blockIdx.y;
+    const int cr = stft_row_re(bin, nb), ci = stft_row_im(bin, nb);
+    const int row = (bin + n_fft / 2) % n_fft;
+    const float4* re4 = reinterpret_cast<const float4*>(csave + cr * ldm);
+    const float4* im4 = reinterpret_cast<const float4*>(csave + ci * ldm);
+    float4* dre4 = reinterpret_cast<float4*>(dC + cr * ldm);
+    float4* dim4 = reinterpret_cast<float4*>(dC + ci * ldm);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; 4 * i < M; i += gridDim.x * blockDim.x) {
+        const float4 r4 = re4[i], i4 = im4[i];                    // rows >= M of the last group are padding: zero gradient
+        const float re[4] = {r4.x, r4.y, r4.z, r4.w}, im[4] = {i4.x, i4.y, i4.z, i4.w};
+        float dr[4], di[4];
+        int seq = (4 * i) / F, f = 4 * i - seq * F;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            dr[j] = 0.f;
+            di[j] = 0.f;
+            if (4 * i + j < M) {
+                const float g = __ldg(gout + ((long long)seq * n_fft + row) * F + f);
+                const float mag = sqrtf(fmaf(re[j], re[j], im[j] * im[j]));
+                const float w = mag > 0.f ? g / ((mag + 1e-6f) * mag) : 0.f;
+                dr[j] = w * re[j];
+                di[j] = w * im[j];
+            }
+            if (++f == F) { f = 0; ++seq; }
+        }
+        dre4[i] = make_float4(dr[0], dr[1], dr[2], dr[3]);
+        dim4[i] = make_float4(di[0], di[1], di[2], di[3]);
     }
 }
-// overlap-add of the frame gradients through the reflect padding: dA (S*F, 2 n_fft) -> grad_iq (S, T, 2), zeroed by the caller
+// overlap-add of the frame gradients through the reflect padding: dA (S*F, 2 n_fft) -> grad_iq (S, T, 2).  Gather form, one
+// thread per output sample and component: padded position u receives dA[frame f][u - f hop] from every frame that covers
+// it, and sample t is the image of u = t + n_fft/2 and of its mirror positions in the two reflected margins.  No atomics,
+// no zero fill; consecutive threads read consecutive columns of the same frame rows.
+__device__ __forceinline__ float stft_fold_at(const float* __restrict__ dA, long long seq, int c, int u, int F, int n_fft, int hop) {
+    // frames f with f hop <= u < f hop + n_fft
+    int f1 = u / hop;
+    f1 = f1 < F - 1 ? f1 : F - 1;
+    int f0 = u - n_fft + 1 <= 0 ? 0 : (u - n_fft + hop) / hop;
+    float acc = 0.f;
+    for (int f = f0; f <= f1; ++f) acc += __ldg(dA + ((seq * F + f) * 2 + c) * (long long)n_fft + (u - f * hop));
+    return acc;
+}
 __global__ void vr_stft_fold_kernel(const float* __restrict__ dA, float* __restrict__ giq, long long S, int T, int F, int n_fft, int hop) {
-    const long long total = S * F * (long long)n_fft;
+    const long long total = S * T;
+    const int h = n_fft / 2, U = T + n_fft;                        // padded length
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int k = (int)(i % n_fft);
-        const long long m = i / n_fft;
-        const int f = (int)(m % F);
-        const long long s = m / F;
-        int t = f * hop - n_fft / 2 + k;
-        t = t < 0 ? -t : t;
-        t = t >= T ? 2 * (T - 1) - t : t;
-        atomicAdd(giq + (s * T + t) * 2, dA[m * 2 * n_fft + k]);
-        atomicAdd(giq + (s * T + t) * 2 + 1, dA[m * 2 * n_fft + n_fft + k]);
+        const long long seq = i / T;
+        const int t = (int)(i - seq * T);
+        float2 g = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int side = 0; side < 3; ++side) {
+            // padded positions that hold sample t: the direct one, the left mirror (u = h - t, 1 <= t <= h) and the right
+            // mirror (u = h + 2 (T - 1) - t, T - 1 - h <= t <= T - 2)
+            const int u = side == 0 ? t + h : (side == 1 ? h - t : h + 2 * (T - 1) - t);
+            const bool on = side == 0 || (side == 1 ? (t >= 1 && t <= h) : (t <= T - 2 && t >= T - 1 - h));
+            if (on && u >= 0 && u < U) {
+                g.x += stft_fold_at(dA, seq, 0, u, F, n_fft, hop);
+                g.y += stft_fold_at(dA, seq, 1, u, F, n_fft, hop);
+            }
+        }
+        reinterpret_cast<float2*>(giq)[i] = g;
     }
 }
 // dBt (2 n_fft, 2 n_fft) -> grad wsin / wcos

@@ -127,7 +127,7 @@ class _GeneralSTFTFunction(torch.autograd.Function):
         need_iq, need_w = ctx.needs_input_grad[0], (ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
         g = gout.contiguous().to(torch.float32)
         dc = torch.empty_like(csave)
-        da = torch.empty_like(frames) if need_iq else None
+        da = torch.empty(N * (T // hop + 1) * 2 * n_fft, dtype=torch.float32, device=dev) if need_iq else None   # frame gradients
         dbt = torch.empty_like(bt) if need_w else None
         giq = torch.empty((N, T, 2), dtype=torch.float32, device=dev) if need_iq else None
         gsin = torch.empty(wshape, dtype=torch.float32, device=dev) if need_w else None
