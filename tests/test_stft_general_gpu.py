@@ -33,7 +33,9 @@ def _oracle(iq, k, n_fft, hop):
 
 @pytest.mark.parametrize("n_fft,hop,T,N,perturb", [(256, 16, 300, 5, 0.0), (256, 16, 300, 40, 0.02), (128, 16, 600, 3, 0.02),
                                                    (512, 32, 700, 3, 0.01), (64, 8, 333, 4, 0.05), (256, 16, 5000, 2, 0.02),
-                                                   (256, 100, 1001, 3, 0.0)])
+                                                   (256, 100, 1001, 3, 0.0),
+                                                   # hop not a multiple of 4 (scalar frame loads), one K block, one frame
+                                                   (64, 6, 250, 3, 0.02), (16, 3, 40, 2, 0.05), (32, 50, 40, 2, 0.02)])
 def test_forward_matches_the_conv1d_restatement(n_fft, hop, T, N, perturb):
     g = torch.Generator().manual_seed(n_fft + T)
     t = torch.arange(T, dtype=torch.float32)[None, :, None]
@@ -55,7 +57,10 @@ def test_forward_matches_the_conv1d_restatement(n_fft, hop, T, N, perturb):
     assert rep["global_abs_over_peak"] <= max(2 * rep_lib["global_abs_over_peak"], 2e-6), (rep["global_abs_over_peak"], rep_lib["global_abs_over_peak"])
 
 
-@pytest.mark.parametrize("n_fft,hop,T,N", [(256, 16, 300, 6), (128, 16, 400, 3), (64, 8, 200, 2)])
+@pytest.mark.parametrize("n_fft,hop,T,N", [(256, 16, 300, 6), (128, 16, 400, 3), (64, 8, 200, 2),
+                                           # unaligned hop, both reflected margins overlapping frames, ragged last K block,
+                                           # and a batch large enough for nine split-K slices
+                                           (64, 6, 203, 2), (32, 5, 77, 3), (256, 16, 300, 300)])
 def test_backward_matches_float64_autograd(n_fft, hop, T, N):
     g = torch.Generator().manual_seed(n_fft)
     iq = torch.randn(N, T, 2, generator=g)
