@@ -935,8 +935,8 @@ int gemm_setup(int dev) {
     static bool done[64] = {false};
     std::lock_guard<std::mutex> lk(mu);
     if (!done[dev]) {
-        CUDA_TRY(cudaFuncSetAttribute(vr::vr_gemm_tf32x3_kernel<1, vr::G_FRAME_ROWS, vr::G_STRIDED>, cudaFuncAttributeMaxDynamicSharedMemorySize, vr::G_SMEM_BYTES));
-        CUDA_TRY(cudaFuncSetAttribute(vr::vr_gemm_tf32x3_kernel<0, vr::G_STRIDED, vr::G_STRIDED>, cudaFuncAttributeMaxDynamicSharedMemorySize, vr::G_SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(vr::vr_gemm_tf32x3_kernel<1, vr::G_FRAME_ROWS, vr::G_TILED>, cudaFuncAttributeMaxDynamicSharedMemorySize, vr::G_SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(vr::vr_gemm_tf32x3_kernel<0, vr::G_STRIDED, vr::G_TILED>, cudaFuncAttributeMaxDynamicSharedMemorySize, vr::G_SMEM_BYTES));
         CUDA_TRY(cudaFuncSetAttribute(vr::vr_gemm_tf32x3_kernel<0, vr::G_STRIDED, vr::G_FRAME_COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, vr::G_SMEM_BYTES));
         done[dev] = true;
     }
@@ -955,12 +955,17 @@ int stft_check(int64_t N, int64_t T, int n_fft, int hop) {
 extern "C" {
 
 static long long stft_ldm(long long M) { return (M + 3) & ~3ll; }
+// floats of one tiled hi / lo image of the (2 n_fft)^2 kernel matrix (vr_stft_gemm.cuh, G_TILED)
+static long long stft_bimg_floats(int n_fft) {
+    const long long K = 2ll * n_fft;
+    return ((K + vr::GN - 1) / vr::GN) * ((K + vr::GK - 1) / vr::GK) * (long long)vr::G_BIMG_FLOATS;
+}
 static long long stft_lp(long long T, int n_fft) { return (T + n_fft + 3) & ~3ll; }     // padded signal length, 16-byte rows
 
 int64_t vr_stft_general_workspace_floats(int64_t N, int64_t T, int32_t n_fft, int32_t hop, int64_t parts[3]) {
     if (N <= 0 || T <= 0 || hop <= 0 || n_fft <= 0) return 0;
     const int64_t M = N * (T / hop + 1), K = 2ll * n_fft;
-    const int64_t a = 2 * N * stft_lp(T, n_fft), b = K * K, c = K * stft_ldm(M);   // padded planar signal (the frames are views of it);       // C / dC: column-major, leading dimension a multiple of 4
+    const int64_t a = 2 * N * stft_lp(T, n_fft), b = 2 * stft_bimg_floats(n_fft), c = K * stft_ldm(M);   // padded planar signal (the frames are views of it);       // C / dC: column-major, leading dimension a multiple of 4
     if (parts) { parts[0] = a; parts[1] = b; parts[2] = c; }
     return a + b + c;
 }
@@ -981,15 +986,17 @@ int vr_stft_general_f32(const float* iq_dev, int64_t N, int64_t T, int32_t n_fft
     const long long M = N * (long long)F;
     const long long Lp = stft_lp(T, n_fft);
     vr::vr_stft_pad_kernel<<<(unsigned)std::min<long long>((N * Lp + 255) / 256, sm_count * 16ll), 256, 0, st>>>(iq_dev, frames_work, N, (int)T, Lp, n_fft);
-    vr::vr_stft_bt_kernel<<<(n_fft * n_fft + 255) / 256, 256, 0, st>>>(wsin_dev, wcos_dev, bt_work, n_fft, nb);
+    const long long img = stft_bimg_floats(n_fft);
+    if (K % vr::GN) CUDA_TRY(cudaMemsetAsync(bt_work, 0, (size_t)(2 * img) * sizeof(float), st));      // rows past K of the one tile
+    vr::vr_stft_bt_kernel<<<(n_fft * n_fft + 255) / 256, 256, 0, st>>>(wsin_dev, wcos_dev, bt_work, bt_work + img, n_fft, nb, (K + vr::GK - 1) / vr::GK);
     vr::GemmParams g;
     memset(&g, 0, sizeof(g));
     g.P = frames_work; g.Lp = Lp; g.hop = hop;       // A = the frames, read as views of the padded signal
-    g.B = bt_work; g.sBn = K; g.sBk = 1;
+    g.Bimg = bt_work;                                // B = the kernel matrix, pre-split and pre-tiled: bulk copies
     g.M = (int)M; g.N = K; g.K = K; g.kb_per_split = (K + vr::GK - 1) / vr::GK;
     g.out = out_dev; g.csave = c_save; g.ldc = stft_ldm(M); g.F = F; g.n_fft = n_fft; g.nb = nb;
     dim3 grid((unsigned)(((M + vr::GM - 1) / vr::GM) * ((K + vr::GN - 1) / vr::GN)));
-    vr::vr_gemm_tf32x3_kernel<1, vr::G_FRAME_ROWS, vr::G_STRIDED><<<grid, vr::G_THREADS, vr::G_SMEM_BYTES, st>>>(g);
+    vr::vr_gemm_tf32x3_kernel<1, vr::G_FRAME_ROWS, vr::G_TILED><<<grid, vr::G_THREADS, vr::G_SMEM_BYTES, st>>>(g);
     CUDA_TRY(cudaGetLastError());
     return VR_OK;
 }
@@ -1018,10 +1025,10 @@ int vr_stft_general_backward_f32(const float* grad_out_dev, const float* frames_
     if (da_work) {                                   // dA[m, k] = sum_n dC[m, n] Bt[n, k]
         memset(&g, 0, sizeof(g));
         g.A = dc_work; g.sAm = 1; g.sAk = ldm;       // dC is column-major: dC(m, n) = dc[n * ldm + m]
-        g.B = bt_work; g.sBn = 1; g.sBk = K;         // B'(n' = k, k' = n) = Bt[n][k]
+        g.Bimg = bt_work + stft_bimg_floats(n_fft);  // B'(n' = k, k' = n) = Bt[n][k]: the transposed image
         g.M = (int)M; g.N = K; g.K = K; g.C = da_work; g.ldc = K; g.kb_per_split = (K + vr::GK - 1) / vr::GK;
         dim3 grid((unsigned)(((M + vr::GM - 1) / vr::GM) * ((K + vr::GN - 1) / vr::GN)));
-        vr::vr_gemm_tf32x3_kernel<0, vr::G_STRIDED, vr::G_STRIDED><<<grid, vr::G_THREADS, vr::G_SMEM_BYTES, st>>>(g);
+        vr::vr_gemm_tf32x3_kernel<0, vr::G_STRIDED, vr::G_TILED><<<grid, vr::G_THREADS, vr::G_SMEM_BYTES, st>>>(g);
         vr::vr_stft_fold_kernel<<<(unsigned)std::min<long long>((N * T + 255) / 256, sm_count * 16ll), 256, 0, st>>>(da_work, grad_iq_dev, N, (int)T, F, n_fft, hop);
     }
     if (dbt_work) {                                  // dBt[n, k] = sum_m dC[m, n] A[m, k]

@@ -12,9 +12,10 @@
 // layers/virtual_radar.py:126-129 with nnAudio's imag = -conv(., wsin) -- come out of the same accumulator row.
 //
 // Kernel (`vr_gemm_tf32x3_kernel`): tcgen05.mma kind::tf32, M = 128 x N = 128 x K = 8 per instruction, accumulators in
-// tensor memory, issued by one thread; operands staged in shared memory by the CTA's 1024 threads in the canonical
-// K-major 128-byte-swizzled layout, three stages, handed over on mbarriers (full: the warps'
-// arrivals; free: tcgen05.commit).
+// tensor memory, issued by one thread; operands in shared memory in the K-major 128-byte-swizzled layout, three
+// stages, handed over on mbarriers (full: the warps' arrivals + the bulk copy's bytes; free: tcgen05.commit).  A -- the
+// frames, read as views of the padded signal, never materialised -- is staged by the CTA's 1024 threads (global ->
+// registers -> TF32 split -> shared); B -- the kernel matrix -- is split and tiled once per call and bulk-copied.
 // float32 accuracy from 10-bit TF32 mantissas by the error-compensated split a = hi + lo (hi = a rounded to TF32,
 // nearest / ties away, lo = a - hi, exact): A.B = Ahi.Bhi + Alo.Bhi + Ahi.Blo -- three MMAs per K step; the dropped lo.lo term is
 // 2^-22 relative.  The tensor core ACCUMULATES with truncation, one truncation per instruction: with all 3 x K/8 = 192
@@ -24,8 +25,8 @@
 // harmless; the epilogue adds the four in float32.  Epilogue from tensor memory (tcgen05.ld 32x32b, one row per thread):
 // either a plain store, or |X| -> ln(|X| + 1e-6) -> fftshift roll (layers/virtual_radar.py:131-133) written straight
 // into the (N, n_fft, F) output, optionally saving Re/Im for the backward pass.
-// The same kernel does the backward GEMMs (operands are addressed through element strides, so transposes cost nothing):
-// dA = dC . Bt (gradient of the frames) and dBt = dC^T . A (gradient of the kernels).
+// The same kernel does the backward GEMMs (operands are addressed through element strides, the frame view or the tiled
+// image, so transposes cost nothing): dA = dC . Bt (gradient of the frames) and dBt = dC^T . A (gradient of the kernels).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -47,6 +48,10 @@ constexpr int G_WARPS = G_THREADS / 32;             // warp w reads accumulator 
 constexpr int G_PARTS = G_THREADS / 128;            // the columns in the epilogue
 constexpr int G_ACC = 4;                            // accumulators in tensor memory (G_ACC * GN = 512 columns)
 constexpr int G_STAGES = 3;
+#ifndef VR_GEMM_AHEAD
+#define VR_GEMM_AHEAD 2
+#endif
+constexpr int G_AHEAD = VR_GEMM_AHEAD;               // K blocks whose global loads are in flight in registers
 constexpr int G_STAGE_BYTES = 2 * (GM + GN) * GK * 4;    // hi + lo of the A and B blocks: 64 KB
 constexpr int G_SMEM_BYTES = G_STAGES * G_STAGE_BYTES + 1024;
 static_assert(GM * (GK / 4) == G_THREADS && GN * (GK / 4) == G_THREADS, "one chunk of each operand per thread");
@@ -64,8 +69,12 @@ struct GemmParams {
     // the frame matrix as a VIEW of the padded signal (operand modes 1 and 2): frame row m = (sequence s, frame f),
     // column k = (component c = k / n_fft, sample j = k % n_fft)  ->  P[(s * 2 + c) * Lp + f * hop + j]
     const float* P; long long Lp; int hop;
+    // operand mode G_TILED (B only): B already split into hi / lo and laid out as the shared-memory image of every
+    // (column tile, K block): img[(tile_n * KB_all + kb) * G_BIMG_FLOATS ...] = [hi 16 KB | lo 16 KB], swizzled
+    const float* Bimg;
 };
-enum { G_STRIDED = 0, G_FRAME_ROWS = 1, G_FRAME_COLS = 2 };
+enum { G_STRIDED = 0, G_FRAME_ROWS = 1, G_FRAME_COLS = 2, G_TILED = 3 };
+constexpr int G_BIMG_FLOATS = 2 * GN * GK;          // floats per (column tile, K block) image
 
 #ifdef __CUDACC__
 __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t saddr) {
@@ -134,6 +143,11 @@ __device__ __forceinline__ void tf32_split(float a, float& hi, float& lo) {
     lo = a - hi;
 }
 
+// float index of element (n, k) of B inside the tiled image, for the hi part (the lo part is GN * GK floats further)
+__host__ __device__ inline long long g_bimg_index(int n, int k, int KB_all) {
+    const int tile_n = n / GN, r = n % GN, kb = k / GK, kk = k % GK, kc = kk >> 2;
+    return ((long long)tile_n * KB_all + kb) * G_BIMG_FLOATS + r * (GK) + ((kc ^ (r & 7)) << 2) + (kk & 3);
+}
 // which 16-byte chunk (row r, K chunk kc) of a block thread c moves.  Shared memory holds a block K-major in the 128-byte
 // swizzle the tensor core reads natively (UMMA layout type SWIZZLE_128B): row r is one 128-byte line (GK = 32 floats), its
 // chunk kc at r * 128 + ((kc ^ (r % 8)) * 16); eight-row groups are 1024 bytes apart.
@@ -305,7 +319,10 @@ struct GLoader<G_FRAME_COLS> {
 // Pipeline.  No CTA-wide barrier inside the K loop (the first versions had one per K block, and the slowest of the 32
 // warps' global loads paced every block: 27 % of the stall samples at the barrier, 16 % at the loads, ncu profiles/r02w):
 //   every warp:  wait free[s] (the MMAs that read stage s are complete) -> split its chunks of block kb into stage s ->
-//                issue the loads of block kb + 2 into registers -> fence.proxy.async -> lane 0 arrives on full[s]
+//                issue the loads of block kb + G_AHEAD into registers -> fence.proxy.async -> lane 0 arrives on full[s]
+//   B of the forward and of the frame-gradient GEMM (the kernel matrix) is not staged by the warps at all: it is split and
+//   tiled once per call (vr_stft_bt_kernel) and one thread bulk-copies the 32 KB image of a block (cp.async.bulk ->
+//   complete_tx on full[s]) as soon as the stage is free.
 //   warp 0 then: lane 0 waits full[s] (all 32 warps have arrived), issues the block's 12 MMAs and commits them to free[s].
 // Warps other than 0 run up to G_STAGES blocks ahead of the tensor core.
 template <int EPI, int AMODE, int BMODE>
@@ -320,7 +337,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) vr_gemm_tf32x3_kernel(const __gr
 
     if (tid == 0) {
         for (int i = 0; i < G_STAGES; ++i) {
-            g_mbar_init(&bar_full[i], G_WARPS);
+            g_mbar_init(&bar_full[i], G_WARPS + (BMODE == G_TILED ? 1 : 0));     // + the bulk copy's expect_tx arrival
             g_mbar_init(&bar_free[i], 1);
         }
         g_mbar_init(&bar_done, 1);
@@ -335,13 +352,22 @@ __global__ void __launch_bounds__(G_THREADS, 1) vr_gemm_tf32x3_kernel(const __gr
     const int KB_all = (p.K + GK - 1) / GK;
     const int kb_first = blockIdx.z * p.kb_per_split;
     const int KB = (KB_all - kb_first < p.kb_per_split) ? (KB_all - kb_first) : p.kb_per_split;     // this slice's K blocks (>= 1)
+    constexpr bool B_TILED = BMODE == G_TILED;                    // B arrives by bulk copy: no registers, no split, no stores
     GLoader<AMODE> la;
-    GLoader<BMODE> lb;
+    GLoader<B_TILED ? G_STRIDED : BMODE> lb;
     la.template init<GM>(p, p.A, p.sAm, p.sAk, m0, p.M, kb_first * GK, tid);
-    lb.template init<GN>(p, p.B, p.sBn, p.sBk, n0, p.N, kb_first * GK, tid);
-    float4 fa0 = la.load(p, p.K), fb0 = lb.load(p, p.K);
-    float4 fa1 = make_float4(0.f, 0.f, 0.f, 0.f), fb1 = fa1;
-    if (KB > 1) { fa1 = la.load(p, p.K); fb1 = lb.load(p, p.K); }
+    // register prefetch: G_AHEAD K blocks in flight (one fragment per stage; the loop is unrolled over the stages)
+    float4 fa0 = la.load(p, p.K), fb0 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 fa1 = fb0, fb1 = fb0, fa2 = fb0, fb2 = fb0;
+    if (KB > 1) fa1 = la.load(p, p.K);
+    if (KB > 2 && G_AHEAD > 2) fa2 = la.load(p, p.K);
+    if (!B_TILED) {
+        lb.template init<GN>(p, p.B, p.sBn, p.sBk, n0, p.N, kb_first * GK, tid);
+        fb0 = lb.load(p, p.K);
+        if (KB > 1) fb1 = lb.load(p, p.K);
+        if (KB > 2 && G_AHEAD > 2) fb2 = lb.load(p, p.K);
+    }
+    const float* bimg = B_TILED ? p.Bimg + ((long long)tile_n * KB_all + kb_first) * G_BIMG_FLOATS : nullptr;
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -351,15 +377,26 @@ __global__ void __launch_bounds__(G_THREADS, 1) vr_gemm_tf32x3_kernel(const __gr
     // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 [4,6), A = B = TF32 [7,10) [10,13), both K-major,
     // N >> 3 at [17,23), M >> 4 at [24,29)
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(GN >> 3) << 17) | ((uint32_t)(GM >> 4) << 24);
-    int s = 0;                                                    // stage of block kb, and how often it has been used before
-    uint32_t use = 0;
-    auto k_block = [&](const int kb, float4& ra, float4& rb) {
+    uint32_t use = 0;                                             // how often the stages have been used before
+    auto k_block = [&](const int kb, const int s, float4& ra, float4& rb) {
         unsigned char* st = gsm + s * G_STAGE_BYTES;
         unsigned char* a_hi = st, *a_lo = st + GM * GK * 4, *b_hi = st + 2 * GM * GK * 4, *b_lo = b_hi + GN * GK * 4;
         if (use > 0) g_mbar_wait(&bar_free[s], (use - 1) & 1);    // the MMAs that read this stage have completed
-        tf32_store_split(a_hi, a_lo, la.off, ra);
-        tf32_store_split(b_hi, b_lo, lb.off, rb);
-        if (kb + 2 < KB) { ra = la.load(p, p.K); rb = lb.load(p, p.K); }       // the block after next: in flight over two blocks
+        if (B_TILED) {
+            if (tid == 32) {                                      // one thread of warp 1 (warp 0 issues the MMAs): 32 KB, hi | lo
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                             ::"r"((uint32_t)__cvta_generic_to_shared(&bar_full[s])), "r"((uint32_t)(G_BIMG_FLOATS * 4)) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"((uint32_t)__cvta_generic_to_shared(b_hi)), "l"(bimg + (long long)kb * G_BIMG_FLOATS),
+                               "r"((uint32_t)(G_BIMG_FLOATS * 4)), "r"((uint32_t)__cvta_generic_to_shared(&bar_full[s])) : "memory");
+            }
+            tf32_store_split(a_hi, a_lo, la.off, ra);
+            if (kb + G_AHEAD < KB) ra = la.load(p, p.K);
+        } else {
+            tf32_store_split(a_hi, a_lo, la.off, ra);
+            tf32_store_split(b_hi, b_lo, lb.off, rb);
+            if (kb + G_AHEAD < KB) { ra = la.load(p, p.K); rb = lb.load(p, p.K); }
+        }       // the block after next: in flight over two blocks
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the tensor core's reads
         __syncwarp();
         if (lane == 0) g_mbar_arrive(&bar_full[s]);
@@ -383,11 +420,24 @@ __global__ void __launch_bounds__(G_THREADS, 1) vr_gemm_tf32x3_kernel(const __gr
             }
             __syncwarp();
         }
-        if (++s == G_STAGES) { s = 0; ++use; }
     };
-    for (int kb = 0; kb < KB; kb += 2) {
-        k_block(kb, fa0, fb0);
-        if (kb + 1 < KB) k_block(kb + 1, fa1, fb1);
+    static_assert(G_STAGES == 3 && (G_AHEAD == 3 || G_AHEAD == 2), "the loop below is written out for three stages");
+    if (G_AHEAD == 3) {
+        for (int kb = 0; kb < KB; kb += 3, ++use) {               // fragment i <-> stage i
+            k_block(kb, 0, fa0, fb0);
+            if (kb + 1 < KB) k_block(kb + 1, 1, fa1, fb1);
+            if (kb + 2 < KB) k_block(kb + 2, 2, fa2, fb2);
+        }
+    } else {
+        for (int kb = 0; kb < KB; kb += 6, ++use) {               // two fragments, three stages: period six
+            k_block(kb, 0, fa0, fb0);
+            if (kb + 1 < KB) k_block(kb + 1, 1, fa1, fb1);
+            if (kb + 2 < KB) k_block(kb + 2, 2, fa0, fb0);
+            ++use;
+            if (kb + 3 < KB) k_block(kb + 3, 0, fa1, fb1);
+            if (kb + 4 < KB) k_block(kb + 4, 1, fa0, fb0);
+            if (kb + 5 < KB) k_block(kb + 5, 2, fa1, fb1);
+        }
     }
     if (KB > 0) g_mbar_wait(&bar_done, 0u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -491,16 +541,27 @@ __global__ void vr_stft_pad_kernel(const float* __restrict__ iq, float* __restri
 // row of Bt that holds Re / Im of `bin` under the column-tile layout [re block | im block] of nb bins
 __host__ __device__ inline int stft_row_re(int bin, int nb) { return (bin / nb) * 2 * nb + bin % nb; }
 __host__ __device__ inline int stft_row_im(int bin, int nb) { return (bin / nb) * 2 * nb + nb + bin % nb; }
-// Bt (2 n_fft, 2 n_fft) from stft.wsin / stft.wcos (n_fft, 1, n_fft)
-__global__ void vr_stft_bt_kernel(const float* __restrict__ wsin, const float* __restrict__ wcos, float* __restrict__ Bt, int n_fft, int nb) {
+// Bt (2 n_fft, 2 n_fft) from stft.wsin / stft.wcos (n_fft, 1, n_fft), never stored as a matrix: written split into TF32
+// hi / lo parts as the tiled shared-memory images the GEMMs bulk-copy -- `fwd` for C = A . Bt^T (B(n, k) = Bt[n][k]) and
+// `bwd` for dA = dC . Bt (B'(k, n) = Bt[n][k]).  K = 2 n_fft; rows beyond K of a 128-row tile stay zero (the host clears).
+__device__ __forceinline__ void stft_bimg_put(float* fwd, float* bwd, int n, int k, float v, int KB_all) {
+    float hi, lo;
+    tf32_split(v, hi, lo);
+    const long long f = g_bimg_index(n, k, KB_all), t = g_bimg_index(k, n, KB_all);
+    fwd[f] = hi; fwd[f + GN * GK] = lo;
+    bwd[t] = hi; bwd[t + GN * GK] = lo;
+}
+__global__ void vr_stft_bt_kernel(const float* __restrict__ wsin, const float* __restrict__ wcos, float* __restrict__ fwd,
+                                  float* __restrict__ bwd, int n_fft, int nb, int KB_all) {
     const int total = n_fft * n_fft;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int bin = i / n_fft, s = i - bin * n_fft;
         const float c = __ldg(wcos + i), sn = __ldg(wsin + i);
-        float* re = Bt + (long long)stft_row_re(bin, nb) * 2 * n_fft;
-        float* im = Bt + (long long)stft_row_im(bin, nb) * 2 * n_fft;
-        re[s] = c; re[n_fft + s] = sn;
-        im[s] = -sn; im[n_fft + s] = c;
+        const int re = stft_row_re(bin, nb), im = stft_row_im(bin, nb);
+        stft_bimg_put(fwd, bwd, re, s, c, KB_all);
+        stft_bimg_put(fwd, bwd, re, n_fft + s, sn, KB_all);
+        stft_bimg_put(fwd, bwd, im, s, -sn, KB_all);
+        stft_bimg_put(fwd, bwd, im, n_fft + s, c, KB_all);
     }
 }
 // backward of ln(|X| + 1e-6) and the roll: dC from grad_out and the saved Re / Im.  C and dC are column-major (2 n_fft
