@@ -175,7 +175,8 @@ int vr_backward_params_f32(const float* x_dev, const float* iq_dev, const float*
  *   out_dev (N, n_fft, T/hop + 1).  Work buffers (sizes from vr_stft_general_workspace_floats: parts[0] the
  *   reflect-padded planar signal -- the frame matrix is never materialised, the GEMM reads the frames as views of it --
  *   parts[1] kernel matrix, parts[2] saved Re/Im): frames_work and bt_work are scratch that the backward pass re-reads;
- *   c_save (optional, NULL = inference) keeps Re / Im of every bin for it.                                          */
+ *   c_save (optional, NULL = inference) keeps Re / Im of every bin for it.  bt_work, c_save (and dc_work below) must be
+ *   16-byte aligned, iq_dev (and grad_iq_dev) 8-byte aligned -- VR_ERR_ARG otherwise: bulk copies, 16-byte accesses.  */
 int64_t vr_stft_general_workspace_floats(int64_t N, int64_t T, int32_t n_fft, int32_t hop, int64_t parts[3]);
 int vr_stft_general_f32(const float* iq_dev, int64_t N, int64_t T, int32_t n_fft, int32_t hop,
                         const float* wsin_dev, const float* wcos_dev, float* frames_work, float* bt_work,

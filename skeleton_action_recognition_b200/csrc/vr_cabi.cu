@@ -942,6 +942,7 @@ int gemm_setup(int dev) {
     }
     return VR_OK;
 }
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }      // nullptr counts as aligned
 int stft_nb(int n_fft) { return n_fft < vr::GN / 2 ? n_fft : vr::GN / 2; }    // bins per column tile: [re block | im block]
 int stft_check(int64_t N, int64_t T, int n_fft, int hop) {
     if (N <= 0 || T <= 0 || hop <= 0) return fail(VR_ERR_SHAPE, "N, T, hop must be positive");
@@ -974,6 +975,8 @@ int vr_stft_general_f32(const float* iq_dev, int64_t N, int64_t T, int32_t n_fft
                         const float* wsin_dev, const float* wcos_dev, float* frames_work, float* bt_work,
                         float* c_save /* may be NULL */, float* out_dev, void* stream) {
     if (!iq_dev || !wsin_dev || !wcos_dev || !frames_work || !bt_work || !out_dev) return fail(VR_ERR_ARG, "device pointers must not be null");
+    if (!aligned16(bt_work) || !aligned16(c_save) || (reinterpret_cast<uintptr_t>(iq_dev) & 7))     // bulk copies, 16-byte column accesses, float2 samples
+        return fail(VR_ERR_ARG, "bt_work and c_save must be 16-byte aligned, iq_dev 8-byte aligned");
     int rc = stft_check(N, T, n_fft, hop);
     if (rc) return rc;
     int dev, sm_count;
@@ -1006,6 +1009,8 @@ int vr_stft_general_backward_f32(const float* grad_out_dev, const float* frames_
                                  float* dc_work, float* da_work /* NULL: no grad_iq */, float* dbt_work /* NULL: no kernel grads */,
                                  float* grad_iq_dev, float* grad_wsin_dev, float* grad_wcos_dev, void* stream) {
     if (!grad_out_dev || !frames_work || !bt_work || !c_save || !dc_work) return fail(VR_ERR_ARG, "device pointers must not be null");
+    if (!aligned16(bt_work) || !aligned16(c_save) || !aligned16(dc_work) || (reinterpret_cast<uintptr_t>(grad_iq_dev) & 7))
+        return fail(VR_ERR_ARG, "bt_work, c_save and dc_work must be 16-byte aligned, grad_iq_dev 8-byte aligned");
     if ((da_work == nullptr) != (grad_iq_dev == nullptr)) return fail(VR_ERR_ARG, "da_work and grad_iq_dev go together");
     if ((dbt_work == nullptr) != (grad_wsin_dev == nullptr) || (dbt_work == nullptr) != (grad_wcos_dev == nullptr))
         return fail(VR_ERR_ARG, "dbt_work, grad_wsin_dev and grad_wcos_dev go together");

@@ -129,6 +129,20 @@ def test_argument_errors(cabi):
         cabi.plan(1, 300, 25, 1, src, dst, hop=0)
 
 
+def test_stft_general_rejects_misaligned_work_buffers(cabi):
+    """Argument validation happens before any CUDA call: fake device addresses are enough (no GPU needed)."""
+    L = cabi.lib()
+    ok = 0x10000                                     # 16-byte aligned, never dereferenced: the call stops at the checks
+    args = lambda bt, cs, iq=ok: (iq, 2, 300, 256, 16, ok, ok, ok, bt, cs, ok, None)      # noqa: E731
+    assert L.vr_stft_general_f32(*args(ok + 4, ok)) == cabi.VR_ERR_ARG
+    assert "16-byte" in cabi.last_error()
+    assert L.vr_stft_general_f32(*args(ok, ok + 8)) == cabi.VR_ERR_ARG
+    assert L.vr_stft_general_f32(*args(ok, None, ok + 4)) == cabi.VR_ERR_ARG
+    assert L.vr_stft_general_f32(*args(None, ok)) == cabi.VR_ERR_ARG           # null work buffer
+    # backward: dc_work misaligned
+    assert L.vr_stft_general_backward_f32(ok, ok, ok, ok, 2, 300, 256, 16, ok + 4, None, None, None, None, None, None) == cabi.VR_ERR_ARG
+
+
 def test_module_surface_matches_reference():
     import torch
     from skeleton_action_recognition_b200 import VirtualRadar, edges
