@@ -42,6 +42,29 @@ def test_dataparallel_replicas_match_single_gpu():
     assert torch.allclose(tl.wavelength.grad, g1[0], rtol=1e-4) and torch.allclose(tl.radar_location.grad, g1[1], rtol=1e-4, atol=1e-6 * g1[1].abs().max())
 
 
+def test_trained_stft_kernels_on_the_second_device_and_under_dataparallel():
+    """The tcgen05 STFT path (per-device kernel attributes, tensor-memory allocation, bulk copies) on cuda:1, and the
+    DataParallel replicas of a layer with trainable kernels: forward bits and kernel gradients as on one GPU."""
+    _need_two()
+    from skeleton_action_recognition_b200 import VirtualRadar
+    x = fx.s1_iid(12)
+    l0 = VirtualRadar(wavelength=5e-4, train_stft_kernel=True, device="cuda:0").to("cuda:0")
+    l1 = VirtualRadar(wavelength=5e-4, train_stft_kernel=True, device="cuda:1").to("cuda:1")
+    y0 = l0(x.cuda(0))
+    y1 = l1(x.cuda(1))
+    assert y1.device.index == 1 and torch.equal(y0.cpu(), y1.cpu())
+    y0.square().mean().backward()
+    y1.square().mean().backward()
+    assert torch.equal(l0.stft.wsin.grad.cpu(), l1.stft.wsin.grad.cpu())
+    g_single = l0.stft.wcos.grad.clone()
+    l0.zero_grad()
+    dp = torch.nn.DataParallel(l0, device_ids=[0, 1])
+    yd = dp(x.cuda(0))
+    assert torch.equal(yd, y0.detach())
+    yd.square().mean().backward()                    # two shards' kernel gradients, reduced onto device 0
+    assert torch.allclose(l0.stft.wcos.grad, g_single, rtol=1e-3, atol=1e-5 * float(g_single.abs().max()))
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
